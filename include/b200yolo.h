@@ -1,0 +1,147 @@
+/*
+ * b200yolo.h -- C ABI of libb200yolo.so: the B200 (sm_100a) detection post-processing path.
+ *
+ * The reference (kanaksharma67/manual-yolo) has no FFI of its own: its scripts reach this path
+ * through the Ultralytics Python API (detect.py:20-21,541; yolo.py:354,361; pipe.py:147,179;
+ * classifier detect.py:121).  The entry points below are what a binding for that seam needs:
+ * one per replaceable upstream function (ultralytics==8.3.176, requirements.txt:95).  The Python
+ * host side (manual_yolo_b200/api.py) binds them with ctypes; INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (e.g. torch tensor.data_ptr());
+ *    the library never allocates, frees or keeps caller memory, and has no mutable global state;
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *  - return 0 = OK, < 0 = argument error detected on the host before any launch,
+ *    > 0 = cudaError_t observed after launch.  b200yolo_strerror() names both kinds;
+ *  - no exceptions, no abort, no CPU fallback.
+ */
+#ifndef B200YOLO_H_
+#define B200YOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200YOLO_VERSION 100 /* 0.1.0 */
+
+enum {
+  B200YOLO_OK = 0,
+  B200YOLO_ERR_NULL = -1,        /* required pointer is NULL */
+  B200YOLO_ERR_SHAPE = -2,       /* non-positive / inconsistent dimension */
+  B200YOLO_ERR_ALIGN = -3,       /* pointer or pitch not aligned as documented */
+  B200YOLO_ERR_UNSUPPORTED = -4, /* outside the implemented envelope (limits below) */
+  B200YOLO_ERR_WORKSPACE = -5,   /* workspace too small: see b200yolo_workspace_bytes */
+  B200YOLO_ERR_RANGE = -6        /* threshold outside [0,1] etc. (UL asserts the same) */
+};
+
+#define B200YOLO_REG_MAX 16      /* DFL bins per box side (ultralytics nn/modules/head.py Detect.reg_max) */
+#define B200YOLO_MAX_LEVELS 3
+#define B200YOLO_MAX_CLASSES 4096
+#define B200YOLO_MAX_SORT 65536  /* candidates per image the sort/NMS kernels accept (cap) */
+
+int b200yolo_version(void);
+const char* b200yolo_strerror(int code);
+
+/* ---- K1: letterbox (+ normalise) ------------------------------------------------------------
+ * Replaces ultralytics/data/augment.py::LetterBox.__call__ (cv2.resize INTER_LINEAR +
+ * cv2.copyMakeBorder value=114) and, for the f32 variant, the rest of
+ * ultralytics/engine/predictor.py::BasePredictor.preprocess (BGR->RGB, HWC->CHW, float, /255),
+ * entered from detect.py:541 / yolo.py:361 / pipe.py:179.
+ * src: B frames of H x W x 3 uint8 (BGR, interleaved), row pitch / frame stride in bytes.
+ * The resized image is new_w x new_h placed at (left, top) inside outW x outH; the host computes
+ * that geometry (manual_yolo_b200/geometry.py, same arithmetic as LetterBox).  Arithmetic is
+ * cv2's 8-bit fixed point (11-bit coefficients), bit-exact for down-scales.
+ *   _u8_to_f32: dst = (B,3,outH,outW) float32, planes R,G,B when swap_rb != 0; value/255 (true division)
+ *   _u8       : dst = (B,outH,outW,3) uint8, channel order preserved (plain LetterBox drop-in) */
+int b200yolo_letterbox_u8_to_f32(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
+                                 int64_t src_batch_stride, float* dst, int outH, int outW, int new_w,
+                                 int new_h, int top, int left, int pad_value, int swap_rb, void* stream);
+int b200yolo_letterbox_u8(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
+                          int64_t src_batch_stride, uint8_t* dst, int outH, int outW, int new_w,
+                          int new_h, int top, int left, int pad_value, void* stream);
+
+/* ---- K2: Detect-head decode + confidence filter + compaction ---------------------------------
+ * Replaces ultralytics/nn/modules/head.py::Detect._inference (DFL softmax expectation,
+ * dist2bbox(xywh) * stride, class sigmoid) fused with the head of
+ * ultralytics/utils/ops.py::non_max_suppression (amax > conf, xywh2xyxy, cls.max, conf filter,
+ * optional `classes` filter).  The head may be the concatenated (B, 64+nc, A) tensor or the three
+ * per-level (B, 64+nc, Hi, Wi) tensors: each level is described by a b200yolo_level. */
+typedef struct b200yolo_level {
+  const float* ptr;        /* element (b, ch, i) lives at ptr[b*batch_stride + ch*chan_stride + i] */
+  int64_t batch_stride;    /* in elements */
+  int64_t chan_stride;     /* in elements */
+  int h, w;                /* feature-map size; anchors are row-major, centre (x+0.5, y+0.5) */
+  float stride;            /* 8 / 16 / 32 */
+} b200yolo_level;
+
+/* cand: (B, cap, 6) float32 rows [x1,y1,x2,y2,score,class] in letterboxed pixels, slot order
+ * arbitrary; cand_anchor: (B, cap) int32 anchor index of each slot; cand_count: (B) int32, MUST be
+ * zeroed by the caller; may exceed cap on overflow (slots beyond cap are dropped, the count is not
+ * clamped so the host can detect it).  class_mask: optional nc-bit allow-list (uint32 words). */
+int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
+                           const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count,
+                           int cap, void* stream);
+
+/* Same outputs from an already decoded UL-format prediction (B, 4+nc(+extra), A): rows 0-3 xywh,
+ * rows 4.. class scores.  This is the non_max_suppression(prediction, ...) drop-in entry. */
+int b200yolo_filter_decoded(const float* pred, int B, int channels, int nc, int A, float conf_thres,
+                            const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count,
+                            int cap, void* stream);
+
+/* ---- K3: per-image sort (score descending, anchor ascending on ties) + max_nms cap ----------
+ * Replaces the stable descending sort inside torchvision.ops.nms and UL's `n > max_nms` cap.
+ * order: (B, cap) int32, order[b][r] = slot of rank r for r < min(count, cap, max_nms).
+ * workspace: b200yolo_workspace_bytes(B, cap) bytes, 16-byte aligned (used when cap exceeds the
+ * shared-memory path). */
+int b200yolo_sort_topk(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap,
+                       int max_nms, int* order, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: class-aware greedy NMS with max_det cap ---------------------------------------------
+ * Replaces `boxes = x[:, :4] + cls * max_wh; i = torchvision.ops.nms(boxes, scores, iou); i[:max_det]`
+ * of ops.non_max_suppression: fp32 class-offset boxes, IoU in fp32, comparison against the DOUBLE
+ * threshold, NaN never suppresses.  out: (B, max_det, 6) rows in kept (score-descending) order;
+ * out_anchor: (B, max_det) anchor indices (UL return_idxs); out_count: (B).
+ * scale: optional (B, 5) float32 {gain, pad_x, pad_y, w0, h0}: when non-NULL the boxes are also
+ * mapped to source pixels as ops.scale_boxes + clip_boxes does ((x - pad) / gain, clamp). */
+int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, const int* order, int B,
+                 int cap, int max_nms, double iou_thres, float max_wh, int agnostic, int max_det,
+                 const float* scale, float* out, int* out_anchor, int* out_count, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* ---- a10: ops.scale_boxes + clip_boxes on a flat (n,>=4) xyxy array (in place) --------------- */
+int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float pad_x, float pad_y,
+                         float w0, float h0, void* stream);
+
+/* ---- K5: ROI crop + resize to size x size (rank-classifier batch) ----------------------------
+ * Replaces detect.py:100-113 safe_crop (after the consumers' int() truncation, detect.py:581) and
+ * ultralytics ClassificationPredictor.preprocess with the checkpoint's transforms
+ * (Resize(size, bilinear, antialias) -> CenterCrop(size) -> ToTensor -> Normalize(0,1)), i.e. Pillow's
+ * two-pass 8-bit fixed-point resample, for every ROI of a batch in one launch (detect.py:121 calls
+ * the predictor once per crop).
+ * frames: (B,H,W,3) uint8 BGR; boxes: (N,4) float32 xyxy source pixels; batch_idx: (N) int32;
+ * roi_count: optional device int32 -- when non-NULL only the first min(*roi_count, N) ROIs are done.
+ * dst: (N,3,size,size) float32 RGB in [0,1]; valid: (N) int32, 0 where safe_crop returns None
+ * (the dst rows of invalid ROIs are zero-filled). */
+int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t pitch,
+                             int64_t batch_stride, const float* boxes, const int* batch_idx,
+                             const int* roi_count, int N, int pad, int size, float* dst, int* valid,
+                             void* stream);
+
+/* Gather the detections of selected classes (the *_rank ids) into a dense ROI list, image-major,
+ * detection order preserved: feeds K5 without a host round trip (detect.py:580-588 loop).
+ * det: (B,max_det,6) from b200yolo_nms (source pixels); roi_boxes: (roi_cap,4); roi_batch:
+ * (roi_cap); roi_det: (roi_cap) detection row index; roi_count: (1) MUST be zeroed by the caller. */
+int b200yolo_select_rois(const float* det, const int* det_count, int B, int max_det,
+                         const uint32_t* class_mask, int nc, float* roi_boxes, int* roi_batch,
+                         int* roi_det, int* roi_count, int roi_cap, void* stream);
+
+size_t b200yolo_workspace_bytes(int B, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200YOLO_H_ */

@@ -1,0 +1,13 @@
+"""manual_yolo_b200 -- B200-native (sm_100a) detection post-processing path of kanaksharma67/manual-yolo.
+
+letterbox -> YOLOv8 Detect-head decode + confidence filter -> sort -> class-aware NMS -> ROI crop/resize,
+hand-written CUDA behind the C ABI of ``include/b200yolo.h`` (``libb200yolo.so``).  See DESIGN.md.
+"""
+
+from . import geometry  # noqa: F401
+from .api import (Candidates, Detections, Workspace, crop_resize_rois, decode_and_filter, filter_decoded,  # noqa: F401
+                  letterbox, nms_candidates, non_max_suppression, preprocess, scale_boxes, scale_params_tensor,
+                  select_rois, sort_candidates)
+from .pipeline import Pipeline, PipelineResult  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,355 @@
+"""Python host side of the B200 detection path: same names / kwargs as the Ultralytics functions the
+reference reaches through ``model(frame)`` (``/root/reference/detect.py:541``, ``yolo.py:361``,
+``pipe.py:179``) and ``rank_model(crop)`` (``detect.py:121``), bound to the hand-written sm_100a
+kernels through the C ABI in ``include/b200yolo.h``.
+
+PyTorch is only the owner of device memory and streams here.  Every function takes CUDA tensors and
+raises on CPU tensors or unsupported modes -- there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib, geometry
+
+REG_MAX = 16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (manual_yolo_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must have dtype {dtype}, got {t.dtype}")
+
+
+def _frames_4d(frames: torch.Tensor):
+    _require_cuda(frames, "frames", torch.uint8)
+    squeeze = frames.dim() == 3
+    if squeeze:
+        frames = frames.unsqueeze(0)
+    if frames.dim() != 4 or frames.shape[-1] != 3:
+        raise ValueError("frames must be (H,W,3) or (B,H,W,3) uint8 BGR")
+    if frames.stride(-1) != 1 or frames.stride(-2) != 3:
+        frames = frames.contiguous()
+    return frames, squeeze
+
+
+def _class_mask(classes, nc, device):
+    """Allow-list -> (ceil(nc/32),) int32 device tensor of bit words (None = all classes)."""
+    if classes is None:
+        return None
+    words = geometry.class_mask_words(classes, nc)
+    return torch.tensor([w - (1 << 32) if w >= (1 << 31) else w for w in words], dtype=torch.int32, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+def letterbox(image, new_shape=(640, 640), auto=False, scale_fill=False, scaleup=True, center=True,
+              stride=32, padding_value=114, out=None):
+    """``LetterBox.__call__`` drop-in: (H,W,3) or (B,H,W,3) uint8 BGR -> letterboxed uint8, same layout."""
+    frames, squeeze = _frames_4d(image)
+    B, H, W, _ = frames.shape
+    g = geometry.letterbox_geometry((H, W), new_shape, auto, scale_fill, scaleup, center, stride)
+    if out is None:
+        out = torch.empty((B, g["out_h"], g["out_w"], 3), dtype=torch.uint8, device=frames.device)
+    lib = _lib.load()
+    rc = lib.b200yolo_letterbox_u8(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0), _ptr(out),
+                                   g["out_h"], g["out_w"], g["new_w"], g["new_h"], g["top"], g["left"],
+                                   int(padding_value), _stream())
+    _lib.check(rc, "letterbox")
+    return out[0] if squeeze else out
+
+
+def preprocess(frames, new_shape=(640, 640), auto=False, scale_fill=False, scaleup=True, center=True,
+               stride=32, padding_value=114, out=None):
+    """``BasePredictor.preprocess`` drop-in, fused: uint8 BGR frames -> (B,3,H,W) fp32 RGB in [0,1]."""
+    frames, _ = _frames_4d(frames)
+    B, H, W, _ = frames.shape
+    g = geometry.letterbox_geometry((H, W), new_shape, auto, scale_fill, scaleup, center, stride)
+    if out is None:
+        out = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=frames.device)
+    elif tuple(out.shape) != (B, 3, g["out_h"], g["out_w"]) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous (B,3,out_h,out_w) float32 tensor")
+    lib = _lib.load()
+    rc = lib.b200yolo_letterbox_u8_to_f32(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0), _ptr(out),
+                                          g["out_h"], g["out_w"], g["new_w"], g["new_h"], g["top"], g["left"],
+                                          int(padding_value), 1, _stream())
+    _lib.check(rc, "preprocess")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Candidates:
+    """Fixed-capacity candidate arrays produced by K2 (slot order arbitrary)."""
+    rows: torch.Tensor      # (B, cap, 6) f32  x1,y1,x2,y2,score,class  (letterboxed px)
+    anchor: torch.Tensor    # (B, cap) i32
+    count: torch.Tensor     # (B,) i32 (may exceed cap on overflow)
+    cap: int
+
+
+def _alloc_candidates(B, cap, device, out: Optional[Candidates]):
+    if out is not None:
+        if out.cap != cap or out.rows.shape[0] != B:
+            raise ValueError("candidate buffers do not match (B, cap)")
+        out.count.zero_()
+        return out
+    return Candidates(torch.empty((B, cap, 6), dtype=torch.float32, device=device),
+                      torch.empty((B, cap), dtype=torch.int32, device=device),
+                      torch.zeros((B,), dtype=torch.int32, device=device), cap)
+
+
+def decode_and_filter(head, strides=(8, 16, 32), conf_thres=0.25, classes=None, in_hw=None, level_hw=None,
+                      cap=None, out: Optional[Candidates] = None) -> Candidates:
+    """Detect-head decode + confidence filter.
+
+    ``head`` is either the concatenated (B, 64+nc, A) fp32 tensor (``Detect._inference``'s ``x_cat``;
+    give ``in_hw`` = letterboxed input (h, w) or ``level_hw``) or the list of per-level
+    (B, 64+nc, Hi, Wi) tensors straight from the Detect convolutions.
+    """
+    if not 0 <= conf_thres <= 1:
+        raise ValueError(f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0")
+    levels = (_lib.Level * 3)()
+    if isinstance(head, (list, tuple)):
+        if len(head) > 3 or len(head) != len(strides):
+            raise ValueError("need one stride per level, at most 3 levels")
+        B, no = head[0].shape[:2]
+        keep = []
+        for l, (x, s) in enumerate(zip(head, strides)):
+            _require_cuda(x, "head level", torch.float32)
+            if x.dim() != 4 or x.shape[0] != B or x.shape[1] != no:
+                raise ValueError("levels must be (B, 64+nc, Hi, Wi) with equal B and channels")
+            x = x if x.is_contiguous() else x.contiguous()
+            keep.append(x)
+            levels[l] = _lib.Level(x.data_ptr(), x.stride(0), x.stride(1), x.shape[2], x.shape[3], float(s))
+        n_levels, A, device = len(head), sum(x.shape[2] * x.shape[3] for x in head), head[0].device
+    else:
+        _require_cuda(head, "head", torch.float32)
+        if head.dim() != 3:
+            raise ValueError("head must be (B, 64+nc, A)")
+        head = head if head.is_contiguous() else head.contiguous()
+        keep = [head]
+        B, no, A = head.shape
+        if level_hw is None:
+            if in_hw is None:
+                raise ValueError("give in_hw=(h,w) of the letterboxed input or level_hw")
+            level_hw = geometry.level_shapes(in_hw[0], in_hw[1], strides)
+        if sum(h * w for h, w in level_hw) != A:
+            raise ValueError(f"level shapes {level_hw} do not add up to A={A}")
+        off = 0
+        for l, ((h, w), s) in enumerate(zip(level_hw, strides)):
+            levels[l] = _lib.Level(head.data_ptr() + 4 * off, head.stride(0), head.stride(1), h, w, float(s))
+            off += h * w
+        n_levels, device = len(level_hw), head.device
+    nc = no - 4 * REG_MAX
+    if nc <= 0:
+        raise ValueError("head needs 64 DFL channels + nc class channels")
+    cap = int(cap or A)
+    cands = _alloc_candidates(B, cap, device, out)
+    mask = _class_mask(classes, nc, device)
+    rc = _lib.load().b200yolo_decode_filter(levels, n_levels, B, nc, float(conf_thres), _ptr(mask), _ptr(cands.rows),
+                                            _ptr(cands.anchor), _ptr(cands.count), cap, _stream())
+    _lib.check(rc, "decode_and_filter")
+    del keep
+    return cands
+
+
+def filter_decoded(prediction, conf_thres=0.25, classes=None, nc=0, cap=None,
+                   out: Optional[Candidates] = None) -> Candidates:
+    """Candidate filter on an already decoded UL-format prediction (B, 4+nc(+extra), A)."""
+    _require_cuda(prediction, "prediction", torch.float32)
+    if prediction.dim() != 3:
+        raise ValueError("prediction must be (B, 4+nc, A)")
+    prediction = prediction if prediction.is_contiguous() else prediction.contiguous()
+    B, ch, A = prediction.shape
+    nc = nc or (ch - 4)
+    cap = int(cap or A)
+    cands = _alloc_candidates(B, cap, prediction.device, out)
+    mask = _class_mask(classes, nc, prediction.device)
+    rc = _lib.load().b200yolo_filter_decoded(_ptr(prediction), B, ch, nc, A, float(conf_thres), _ptr(mask),
+                                             _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), cap, _stream())
+    _lib.check(rc, "filter_decoded")
+    return cands
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 + K4
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Detections:
+    """Padded NMS output: rows [x1,y1,x2,y2,conf,cls]; only the first count[b] rows of image b are valid."""
+    rows: torch.Tensor      # (B, max_det, 6) f32
+    anchor: torch.Tensor    # (B, max_det) i32 (original anchor index: UL return_idxs)
+    count: torch.Tensor     # (B,) i32
+
+    def to_list(self, return_idxs=False):
+        """Ragged ``list[Tensor(n_i, 6)]`` as ``ops.non_max_suppression`` returns (one D2H of counts)."""
+        counts = self.count.tolist()
+        out = [self.rows[b, :n] for b, n in enumerate(counts)]
+        if return_idxs:
+            return out, [self.anchor[b, :n].to(torch.int64) for b, n in enumerate(counts)]
+        return out
+
+
+class Workspace:
+    """Caller-owned scratch for sort/NMS (order array + oversize-image spill)."""
+
+    def __init__(self, B, cap, max_det, device):
+        self.B, self.cap, self.max_det = B, cap, max_det
+        self.order = torch.empty((B, cap), dtype=torch.int32, device=device)
+        nbytes = int(_lib.load().b200yolo_workspace_bytes(B, cap))
+        self.ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=device)
+        self.det = Detections(torch.empty((B, max_det, 6), dtype=torch.float32, device=device),
+                              torch.empty((B, max_det), dtype=torch.int32, device=device),
+                              torch.empty((B,), dtype=torch.int32, device=device))
+
+
+def sort_candidates(cands: Candidates, max_nms=30000, ws: Optional[Workspace] = None) -> Workspace:
+    B = cands.rows.shape[0]
+    ws = ws or Workspace(B, cands.cap, 300, cands.rows.device)
+    rc = _lib.load().b200yolo_sort_topk(_ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), B, cands.cap,
+                                        int(max_nms), _ptr(ws.order), _ptr(ws.ws), ws.ws.numel(), _stream())
+    _lib.check(rc, "sort_candidates")
+    return ws
+
+
+def nms_candidates(cands: Candidates, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680,
+                   scale: Optional[torch.Tensor] = None, ws: Optional[Workspace] = None) -> Detections:
+    """K3 + K4 on K2's candidates.  ``scale``: optional (B,5) f32 {gain,pad_x,pad_y,w0,h0} -> source pixels."""
+    if not 0 <= iou_thres <= 1:
+        raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
+    B = cands.rows.shape[0]
+    if ws is None or ws.max_det != max_det or ws.cap != cands.cap or ws.B != B:
+        ws = Workspace(B, cands.cap, max_det, cands.rows.device)
+    sort_candidates(cands, max_nms, ws)
+    rc = _lib.load().b200yolo_nms(_ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), _ptr(ws.order), B,
+                                  cands.cap, int(max_nms), float(iou_thres), float(max_wh), int(bool(agnostic)),
+                                  int(max_det), _ptr(scale), _ptr(ws.det.rows), _ptr(ws.det.anchor),
+                                  _ptr(ws.det.count), _ptr(ws.ws), ws.ws.numel(), _stream())
+    _lib.check(rc, "nms_candidates")
+    return ws.det
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
+                        multi_label=False, labels=(), max_det=300, nc=0, max_time_img=0.05, max_nms=30000,
+                        max_wh=7680, in_place=True, rotated=False, end2end=False, return_idxs=False):
+    """Drop-in for ``ultralytics.utils.ops.non_max_suppression`` (detect task) on a CUDA prediction.
+
+    Same signature and return value (``list[Tensor(n_i, 6)]``, or ``(output, keepi)`` with
+    ``return_idxs``).  Differences, all documented in DESIGN.md: the input is never modified
+    (``in_place`` is accepted and ignored), the upstream wall-clock ``max_time_img`` break is not
+    replicated, and ``multi_label`` / ``labels`` / ``rotated`` / ``end2end`` / extra mask channels
+    raise ``NotImplementedError`` instead of silently falling back.
+    """
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    if isinstance(prediction, (list, tuple)):
+        prediction = prediction[0]
+    if rotated or end2end or labels:
+        raise NotImplementedError("rotated / end2end / labels are outside the reference's call pattern")
+    _require_cuda(prediction, "prediction")
+    nc = nc or (prediction.shape[1] - 4)
+    if multi_label and nc > 1:
+        raise NotImplementedError("multi_label=True is not implemented (the reference never sets it)")
+    if prediction.shape[1] - nc - 4 != 0:
+        raise NotImplementedError("extra mask channels (segment/pose) are outside this path")
+    cands = filter_decoded(prediction.float(), conf_thres, classes, nc)
+    det = nms_candidates(cands, iou_thres, agnostic, max_det, max_nms, max_wh)
+    out = det.to_list(return_idxs)
+    if return_idxs:
+        return [o.clone() for o in out[0]], out[1]
+    return [o.clone() for o in out]
+
+
+# ------------------------------------------------------------------------------------------------
+# a10
+# ------------------------------------------------------------------------------------------------
+def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xywh=False):
+    """``ops.scale_boxes`` (+ ``clip_boxes``) drop-in on a CUDA (n, >=4) xyxy tensor, in place."""
+    if xywh or not padding:
+        raise NotImplementedError("xywh=True / padding=False are outside the reference's call pattern")
+    _require_cuda(boxes, "boxes", torch.float32)
+    if boxes.dim() != 2 or boxes.shape[1] < 4 or boxes.stride(1) != 1:
+        raise ValueError("boxes must be (n, >=4) float32 with unit inner stride")
+    gain, pad = geometry.scale_boxes_params(img1_shape, img0_shape, ratio_pad)
+    rc = _lib.load().b200yolo_scale_boxes(_ptr(boxes), boxes.shape[0], boxes.stride(0) if boxes.shape[0] else 4,
+                                          float(gain), float(pad[0]), float(pad[1]), float(img0_shape[1]),
+                                          float(img0_shape[0]), _stream())
+    _lib.check(rc, "scale_boxes")
+    return boxes
+
+
+def scale_params_tensor(img1_shape, img0_shapes: Sequence, device):
+    """(B,5) {gain, pad_x, pad_y, w0, h0} rows for the fused rescale inside the NMS kernel."""
+    rows = []
+    for s0 in img0_shapes:
+        gain, pad = geometry.scale_boxes_params(img1_shape, s0)
+        rows.append([gain, pad[0], pad[1], s0[1], s0[0]])
+    return torch.tensor(rows, dtype=torch.float32, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5
+# ------------------------------------------------------------------------------------------------
+def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=None, out=None, valid=None):
+    """Batched ``safe_crop`` + classifier preprocessing: returns ((N,3,size,size) fp32 RGB, valid (N,) i32).
+
+    ``boxes_xyxy``: (N,4) fp32 source-pixel boxes (``int()`` truncation happens on the device, as
+    ``detect.py:581`` does on the host); ``batch_idx``: (N,) int32 frame index.  ``valid`` is 0 where
+    ``safe_crop`` would return None and -1 where the ROI is larger than the kernel's envelope.
+    """
+    frames, _ = _frames_4d(frames)
+    _require_cuda(boxes_xyxy, "boxes_xyxy", torch.float32)
+    _require_cuda(batch_idx, "batch_idx", torch.int32)
+    boxes_xyxy = boxes_xyxy.contiguous()
+    batch_idx = batch_idx.contiguous()
+    N = boxes_xyxy.shape[0]
+    if boxes_xyxy.dim() != 2 or boxes_xyxy.shape[1] != 4 or batch_idx.shape != (N,):
+        raise ValueError("boxes_xyxy must be (N,4) and batch_idx (N,)")
+    B, H, W, _ = frames.shape
+    if out is None:
+        out = torch.empty((N, 3, size, size), dtype=torch.float32, device=frames.device)
+    if valid is None:
+        valid = torch.empty((N,), dtype=torch.int32, device=frames.device)
+    rc = _lib.load().b200yolo_roi_crop_resize(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0),
+                                              _ptr(boxes_xyxy), _ptr(batch_idx), _ptr(roi_count), N, int(pad),
+                                              int(size), _ptr(out), _ptr(valid), _stream())
+    _lib.check(rc, "crop_resize_rois")
+    return out, valid
+
+
+def select_rois(det: Detections, classes, nc, roi_cap, out=None):
+    """Device-side gather of the detections whose class is in ``classes`` (the ``*_rank`` ids).
+
+    Returns (roi_boxes (cap,4) f32, roi_batch (cap,) i32, roi_det (cap,) i32, roi_count (1,) i32)."""
+    B, max_det, _ = det.rows.shape
+    dev = det.rows.device
+    mask = _class_mask(classes, nc, dev)
+    if out is None:
+        out = (torch.empty((roi_cap, 4), dtype=torch.float32, device=dev),
+               torch.empty((roi_cap,), dtype=torch.int32, device=dev),
+               torch.empty((roi_cap,), dtype=torch.int32, device=dev),
+               torch.zeros((1,), dtype=torch.int32, device=dev))
+    else:
+        out[3].zero_()
+    rc = _lib.load().b200yolo_select_rois(_ptr(det.rows), _ptr(det.count), B, max_det, _ptr(mask), int(nc),
+                                          _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), int(roi_cap),
+                                          _stream())
+    _lib.check(rc, "select_rois")
+    return out

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Build libb200yolo.so in-tree for sm_100a.  Usage: manual_yolo_b200/csrc/build.sh [extra nvcc flags]
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include $ARCH"
+OUT="$ROOT/manual_yolo_b200/libb200yolo.so"
+mkdir -p "$HERE/_obj"
+# parity-critical fp32 kernels: no FMA contraction (every add/mul rounds like the torch CPU ops)
+for f in decode_filter nms; do
+  "$NVCC" $COMMON -fmad=false "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
+done
+for f in abi letterbox sort_topk roi; do
+  "$NVCC" $COMMON "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
+done
+wait
+"$NVCC" -shared $ARCH -o "$OUT" "$HERE"/_obj/{abi,letterbox,decode_filter,sort_topk,nms,roi}.o
+echo "built $OUT"

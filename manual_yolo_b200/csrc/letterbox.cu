@@ -1,0 +1,225 @@
+// K1: fused letterbox (cv2 INTER_LINEAR 8-bit fixed point) + pad + BGR->RGB + /255 + NCHW.
+//
+// Replaces ultralytics LetterBox.__call__ + BasePredictor.preprocess (reference entry
+// detect.py:541, yolo.py:361, pipe.py:179); arithmetic restated in oracle/letterbox.py
+// (SURVEY.md Appendix B.1).
+//
+// One CTA produces one output row of one frame.  The (at most two) source rows the bilinear taps
+// reference are staged in shared memory by the TMA engine (cp.async.bulk, 1-D, mbarrier
+// completion) when the row is 16-byte aligned, else by cooperative loads; while the copy is in
+// flight every thread derives its own horizontal taps (double/float arithmetic exactly as
+// cv::resize builds its tables).  Each thread then emits 4 output pixels: three 128-bit streaming
+// stores into the planar fp32 image (or 12 interleaved bytes for the u8 variant).
+// HBM-bound: algorithmic bytes per frame = referenced rows * W*3 + 3*outH*outW*4.
+
+#include "common.cuh"
+
+namespace {
+
+struct LbParams {
+  const uint8_t* src;
+  void* dst;
+  int64_t pitch, bstride;
+  double scale_x, scale_y;
+  int H, W, outH, outW, new_w, new_h, top, left, pad_value, swap_rb;
+  int row_bytes;      // W*3
+  int row_smem;       // bytes reserved per staged row (>= row_bytes + 16, multiple of 16)
+  int bulk_ok;        // rows are 16-byte aligned and row_bytes % 16 == 0
+};
+
+// cv::resize table entry for one axis: source index and 11-bit weights (a0 for s, a1 for s+1).
+__device__ __forceinline__ void cv_linear_tap(int d, double scale, int ssize, int& s, int& a0, int& a1) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+// 6 consecutive bytes (two BGR pixels) starting at byte offset `off` of a staged row.
+__device__ __forceinline__ void load6(const uint8_t* row, int off, uint32_t& lo, uint32_t& hi) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + (off >> 2);
+  uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  uint32_t sh = (off & 3) * 8;
+  lo = __funnelshift_r(w0, w1, sh);
+  hi = __funnelshift_r(w1, w2, sh);
+}
+
+template <typename OutT>
+__device__ __forceinline__ OutT lb_cast(int v);
+template <>
+__device__ __forceinline__ float lb_cast<float>(int v) { return b200::u8_div255(v); }
+template <>
+__device__ __forceinline__ uint8_t lb_cast<uint8_t>(int v) { return (uint8_t)v; }
+
+template <typename OutT>
+__device__ __forceinline__ void store_px4(const LbParams& p, int b, int oy, int ox, const OutT (&v)[4][3], int n) {
+  if constexpr (sizeof(OutT) == 4) {
+    float* base = reinterpret_cast<float*>(p.dst) + ((int64_t)b * 3 * p.outH + oy) * p.outW + ox;
+    const int64_t plane = (int64_t)p.outH * p.outW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float* q = base + (p.swap_rb ? 2 - c : c) * plane;
+      if (n == 4 && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+        b200::stg_stream_f4(q, make_float4(v[0][c], v[1][c], v[2][c], v[3][c]));
+      } else {
+        for (int k = 0; k < n; ++k) q[k] = v[k][c];
+      }
+    }
+  } else {
+    uint8_t* q = reinterpret_cast<uint8_t*>(p.dst) + (((int64_t)b * p.outH + oy) * p.outW + ox) * 3;
+    if (n == 4 && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+      uint32_t w0 = v[0][0] | (v[0][1] << 8) | (v[0][2] << 16) | (v[1][0] << 24);
+      uint32_t w1 = v[1][1] | (v[1][2] << 8) | (v[2][0] << 16) | (v[2][1] << 24);
+      uint32_t w2 = v[2][2] | (v[3][0] << 8) | (v[3][1] << 16) | (v[3][2] << 24);
+      uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+      qw[0] = w0; qw[1] = w1; qw[2] = w2;
+    } else {
+      for (int k = 0; k < n; ++k)
+        for (int c = 0; c < 3; ++c) q[k * 3 + c] = v[k][c];
+    }
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) letterbox_kernel(const LbParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int oy = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const OutT padv = lb_cast<OutT>(p.pad_value);
+
+  const bool interior = (oy >= p.top) && (oy < p.top + p.new_h);
+  int sy = 0, b0 = 2048, b1 = 0;
+  if (interior) cv_linear_tap(oy - p.top, p.scale_y, p.H, sy, b0, b1);
+  const bool two_rows = interior && (b1 != 0);
+  uint8_t* row0 = smem;
+  uint8_t* row1 = smem + p.row_smem;
+
+  if (interior) {
+    const uint8_t* g0 = p.src + (int64_t)b * p.bstride + (int64_t)sy * p.pitch;
+    const uint8_t* g1 = p.src + (int64_t)b * p.bstride + (int64_t)min(sy + 1, p.H - 1) * p.pitch;
+    if (p.bulk_ok) {
+      if (tid == 0) {
+        b200::mbar_init(&bar, 1);
+        b200::mbar_fence_init();
+        b200::mbar_expect_tx(&bar, two_rows ? 2u * p.row_bytes : (uint32_t)p.row_bytes);
+        b200::bulk_g2s(row0, g0, p.row_bytes, &bar);
+        if (two_rows) b200::bulk_g2s(row1, g1, p.row_bytes, &bar);
+      }
+    } else {
+      for (int i = tid; i < p.row_bytes; i += blockDim.x) {
+        row0[i] = g0[i];
+        if (two_rows) row1[i] = g1[i];
+      }
+    }
+  }
+
+  // horizontal taps of this thread's first pixel group are derived while the copy is in flight
+  const int groups = (p.outW + 3) >> 2;
+  int g = tid;
+  bool have = g < groups;
+  int sx[4], a0[4], a1[4];
+  bool in[4];
+  auto taps = [&](int grp) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ox = grp * 4 + k;
+      in[k] = interior && (ox >= p.left) && (ox < p.left + p.new_w);
+      sx[k] = 0; a0[k] = 0; a1[k] = 0;
+      if (in[k]) cv_linear_tap(ox - p.left, p.scale_x, p.W, sx[k], a0[k], a1[k]);
+    }
+  };
+  if (have) taps(g);
+  if (interior) {          // CTA-uniform
+    __syncthreads();       // staged rows (fallback path) / mbarrier init (bulk path) visible
+    if (p.bulk_ok) b200::mbar_wait(&bar, 0);
+  }
+  while (have) {
+    const int ox0 = g * 4;
+    const int n = min(4, p.outW - ox0);
+    OutT v[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!in[k]) {
+        v[k][0] = v[k][1] = v[k][2] = padv;
+        continue;
+      }
+      uint32_t lo, hi;
+      load6(row0, sx[k] * 3, lo, hi);
+      int S0[3], S1[3] = {0, 0, 0};
+      S0[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
+      S0[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
+      S0[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
+      if (two_rows) {
+        load6(row1, sx[k] * 3, lo, hi);
+        S1[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
+        S1[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
+        S1[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int r = (((b0 * (S0[c] >> 4)) >> 16) + ((b1 * (S1[c] >> 4)) >> 16) + 2) >> 2;
+        v[k][c] = lb_cast<OutT>(r);
+      }
+    }
+    store_px4<OutT>(p, b, oy, ox0, v, n);
+    g += blockDim.x;
+    have = g < groups;
+    if (have) taps(g);
+  }
+}
+
+template <typename OutT>
+int launch_letterbox(const uint8_t* src, int B, int H, int W, int64_t pitch, int64_t bstride, void* dst,
+                     int outH, int outW, int new_w, int new_h, int top, int left, int pad_value, int swap_rb,
+                     void* stream) {
+  B200_REQUIRE(src && dst, B200YOLO_ERR_NULL);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0 && new_w > 0 && new_h > 0, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(top >= 0 && left >= 0 && top + new_h <= outH && left + new_w <= outW, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(pitch >= (int64_t)W * 3 && bstride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(pad_value >= 0 && pad_value <= 255, B200YOLO_ERR_RANGE);
+  B200_REQUIRE(B <= 65535 && outH <= 2147483647, B200YOLO_ERR_UNSUPPORTED);
+  LbParams p;
+  p.src = src; p.dst = dst; p.pitch = pitch; p.bstride = bstride;
+  p.H = H; p.W = W; p.outH = outH; p.outW = outW; p.new_w = new_w; p.new_h = new_h;
+  p.top = top; p.left = left; p.pad_value = pad_value; p.swap_rb = swap_rb;
+  // cv::resize: inv_scale = dsize/ssize (double); scale = 1/inv_scale
+  p.scale_x = 1.0 / ((double)new_w / (double)W);
+  p.scale_y = 1.0 / ((double)new_h / (double)H);
+  p.row_bytes = W * 3;
+  p.row_smem = ((p.row_bytes + 15) / 16) * 16 + 16;
+  p.bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (pitch % 16 == 0) && (bstride % 16 == 0) &&
+              (p.row_bytes % 16 == 0);
+  const size_t smem = 2 * (size_t)p.row_smem;
+  B200_REQUIRE(smem <= 200 * 1024, B200YOLO_ERR_UNSUPPORTED);
+  auto kern = letterbox_kernel<OutT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int groups = (outW + 3) / 4;
+  int threads = ((groups + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  dim3 grid(outH, B);
+  kern<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  return b200_launch_status();
+}
+
+}  // namespace
+
+extern "C" int b200yolo_letterbox_u8_to_f32(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
+                                            int64_t src_batch_stride, float* dst, int outH, int outW,
+                                            int new_w, int new_h, int top, int left, int pad_value,
+                                            int swap_rb, void* stream) {
+  return launch_letterbox<float>(src, B, H, W, src_pitch, src_batch_stride, dst, outH, outW, new_w, new_h, top,
+                                 left, pad_value, swap_rb, stream);
+}
+
+extern "C" int b200yolo_letterbox_u8(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
+                                     int64_t src_batch_stride, uint8_t* dst, int outH, int outW, int new_w,
+                                     int new_h, int top, int left, int pad_value, void* stream) {
+  return launch_letterbox<uint8_t>(src, B, H, W, src_pitch, src_batch_stride, dst, outH, outW, new_w, new_h, top,
+                                   left, pad_value, 0, stream);
+}

@@ -1,0 +1,224 @@
+// K4: class-aware greedy NMS with max_det cap (+ optional rescale to source pixels).
+//
+// Replaces, in ultralytics ops.non_max_suppression (reference entry detect.py:541 / yolo.py:361 /
+// pipe.py:179):   c = x[:, 5:6] * (0 if agnostic else max_wh); boxes = x[:, :4] + c
+//                 i = torchvision.ops.nms(boxes, scores, iou_thres); i = i[:max_det]; x[i]
+// and optionally ops.scale_boxes + clip_boxes.  Restated in oracle/nms.py (nms_numpy_restated follows
+// torchvision's CPU nms_kernel: SURVEY.md Appendix A.9 / B.2 / B.7).
+//
+// Bit-exactness rules implemented here:
+//   * offset boxes are formed in fp32, fl32(box + fl32(cls * max_wh)), BEFORE areas / IoU;
+//   * inter = max(0, xx2-xx1) * max(0, yy2-yy1); ovr = inter / (ai + aj - inter) with IEEE
+//     division; the fp32 ovr is compared against the DOUBLE threshold; NaN (0/0) never suppresses;
+//   * kept boxes come out in score order, so stopping after max_det keeps == `i[:max_det]`.
+//
+// One CTA per image; sorted offset boxes live in shared memory.  Boxes are processed in chunks of 64
+// (sorted order): (A) the 64x64 intra-chunk IoU bitmask is built in parallel (4 pairs per thread,
+// rows merged with warp shuffles), (B) one thread resolves the chunk serially over the mask words
+// (ffs over the alive bits), (C) the chunk's kept boxes are applied to every later box in parallel.
+// Total IoU work <= kept * n instead of n^2/2.  Compiled with -fmad=false.
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kChunk = 64;
+constexpr int kSmemBoxesMax = 12288;
+
+__device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_a, const float4 b, const double thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  if (!(inter > 0.f)) return false;  // ovr is 0, -0 or NaN: never > thr (thr >= 0)
+  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return (double)ovr > thr;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
+                                                 const int* __restrict__ cand_count, const int* __restrict__ order,
+                                                 int cap, int max_nms, double thr, float max_wh, int agnostic,
+                                                 int max_det, const float* __restrict__ scale,
+                                                 float* __restrict__ out, int* __restrict__ out_anchor,
+                                                 int* __restrict__ out_count, float4* __restrict__ ws, int smem_boxes) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float4* sbox = reinterpret_cast<float4*>(smem_raw);
+  uint8_t* removed = reinterpret_cast<uint8_t*>(sbox + smem_boxes);   // [smem_boxes or n]
+  int* keep = reinterpret_cast<int*>(removed + ((smem_boxes + 15) & ~15));  // [max_det]
+  __shared__ unsigned long long mask[kChunk];
+  __shared__ unsigned rem_bits[2];
+  __shared__ unsigned long long kept_bits_s;
+  __shared__ int kcount_s;
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = min(min(min(cand_count[b], cap), max_nms), B200YOLO_MAX_SORT);
+  const float* crow = cand + (int64_t)b * cap * 6;
+  const int* orow = order + (int64_t)b * cap;
+  if (n <= 0) {
+    if (tid == 0) out_count[b] = 0;
+    return;
+  }
+  float4* box = sbox;
+  uint8_t* rem = removed;
+  if (n > smem_boxes) {  // oversize image: boxes + flags in the workspace (L2-resident)
+    box = ws + (int64_t)b * (cap + (cap + 15) / 16);
+    rem = reinterpret_cast<uint8_t*>(box + cap);
+  }
+  for (int r = tid; r < n; r += NT) {
+    const float* row = crow + (int64_t)orow[r] * 6;
+    const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
+    box[r] = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
+    rem[r] = 0;
+  }
+  if (tid == 0) kcount_s = 0;
+  __syncthreads();
+
+  for (int s = 0; s < n; s += kChunk) {
+    const int m = min(kChunk, n - s);
+    // ---- (A) intra-chunk mask: thread -> row i = t/16, columns j = (t%16)*4 .. +3 ----
+    for (int t = tid; t < kChunk * 16; t += NT) {
+      const int i = t >> 4, jg = t & 15;
+      unsigned nib = 0;
+      if (i < m) {
+        const float4 bi = box[s + i];
+        const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = jg * 4 + u;
+          if (j > i && j < m && iou_suppresses(bi, ai, box[s + j], thr)) nib |= 1u << u;
+        }
+      }
+      unsigned lo = jg < 8 ? nib << (jg * 4) : 0u;
+      unsigned hi = jg >= 8 ? nib << ((jg - 8) * 4) : 0u;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+        hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+      }
+      if (jg == 0) mask[i] = ((unsigned long long)hi << 32) | lo;
+    }
+    if (wid < 2) {
+      const int j = wid * 32 + lane;
+      const unsigned bits = __ballot_sync(0xffffffffu, j < m && rem[s + j] != 0);
+      if (lane == 0) rem_bits[wid] = bits;
+    }
+    __syncthreads();
+    // ---- (B) serial resolve of the chunk ----
+    if (tid == 0) {
+      const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+      unsigned long long alive = valid & ~(((unsigned long long)rem_bits[1] << 32) | rem_bits[0]);
+      unsigned long long kept = 0;
+      int kc = kcount_s;
+      while (alive && kc < max_det) {
+        const int i = __ffsll((long long)alive) - 1;
+        kept |= 1ull << i;
+        keep[kc++] = s + i;
+        alive &= ~mask[i];
+        alive &= ~(1ull << i);
+      }
+      kept_bits_s = kept;
+      kcount_s = kc;
+    }
+    __syncthreads();
+    const int kc = kcount_s;
+    if (kc >= max_det) break;
+    // ---- (C) apply this chunk's kept boxes to all later boxes ----
+    const unsigned long long kept = kept_bits_s;
+    if (kept) {
+      for (int j = s + kChunk + tid; j < n; j += NT) {
+        if (rem[j]) continue;
+        const float4 bj = box[j];
+        unsigned long long kb = kept;
+        while (kb) {
+          const int i = __ffsll((long long)kb) - 1;
+          kb &= kb - 1;
+          const float4 bi = box[s + i];
+          const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+          if (iou_suppresses(bi, ai, bj, thr)) { rem[j] = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- outputs: un-offset rows in kept order ----
+  const int kc = kcount_s;
+  float gain = 1.f, padx = 0.f, pady = 0.f, w0 = 0.f, h0 = 0.f;
+  if (scale) { gain = scale[b * 5 + 0]; padx = scale[b * 5 + 1]; pady = scale[b * 5 + 2]; w0 = scale[b * 5 + 3]; h0 = scale[b * 5 + 4]; }
+  for (int r = tid; r < kc; r += NT) {
+    const int slot = orow[keep[r]];
+    const float* row = crow + (int64_t)slot * 6;
+    float x1 = row[0], y1 = row[1], x2 = row[2], y2 = row[3];
+    if (scale) {
+      x1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x1, padx), gain), 0.f), w0);
+      y1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y1, pady), gain), 0.f), h0);
+      x2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x2, padx), gain), 0.f), w0);
+      y2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y2, pady), gain), 0.f), h0);
+    }
+    float* o = out + ((int64_t)b * max_det + r) * 6;
+    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = row[4]; o[5] = row[5];
+    out_anchor[(int64_t)b * max_det + r] = cand_anchor[(int64_t)b * cap + slot];
+  }
+  if (tid == 0) out_count[b] = kc;
+}
+
+__global__ void scale_boxes_kernel(float* boxes, int n, int row_stride, float gain, float padx, float pady,
+                                   float w0, float h0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* r = boxes + (int64_t)i * row_stride;
+  r[0] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[0], padx), gain), 0.f), w0);
+  r[1] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[1], pady), gain), 0.f), h0);
+  r[2] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[2], padx), gain), 0.f), w0);
+  r[3] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[3], pady), gain), 0.f), h0);
+}
+
+}  // namespace
+
+extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, const int* order,
+                            int B, int cap, int max_nms, double iou_thres, float max_wh, int agnostic, int max_det,
+                            const float* scale, float* out, int* out_anchor, int* out_count, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(cand && cand_anchor && cand_count && order && out && out_anchor && out_count, B200YOLO_ERR_NULL);
+  B200_REQUIRE(B > 0 && cap > 0 && max_nms > 0 && max_det > 0, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(cap <= B200YOLO_MAX_SORT && max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
+  B200_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, B200YOLO_ERR_RANGE);
+  if (cap > kSmemBoxesMax) {
+    B200_REQUIRE(workspace, B200YOLO_ERR_NULL);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
+    B200_REQUIRE(workspace_bytes >= (size_t)B * ((size_t)cap + (cap + 15) / 16) * 16, B200YOLO_ERR_WORKSPACE);
+  }
+  const int smem_boxes = cap < kSmemBoxesMax ? cap : kSmemBoxesMax;
+  const size_t smem = (size_t)smem_boxes * 16 + (((size_t)smem_boxes + 15) & ~(size_t)15) + (size_t)max_det * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cap <= 1024) {
+    constexpr int NT = 256;
+    auto kern = nms_kernel<NT>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
+                             max_det, scale, out, out_anchor, out_count, (float4*)workspace, smem_boxes);
+  } else {
+    constexpr int NT = 1024;
+    auto kern = nms_kernel<NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
+                             max_det, scale, out, out_anchor, out_count, (float4*)workspace, smem_boxes);
+  }
+  return b200_launch_status();
+}
+
+extern "C" int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float pad_x, float pad_y,
+                                    float w0, float h0, void* stream) {
+  B200_REQUIRE(boxes, B200YOLO_ERR_NULL);
+  B200_REQUIRE(n >= 0 && row_stride >= 4 && gain > 0.f, B200YOLO_ERR_SHAPE);
+  if (n == 0) return B200YOLO_OK;
+  scale_boxes_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boxes, n, row_stride, gain, pad_x, pad_y,
+                                                                        w0, h0);
+  return b200_launch_status();
+}

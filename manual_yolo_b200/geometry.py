@@ -1,0 +1,70 @@
+"""Host-side geometry of the detection path (pure Python, no device work).
+
+Mirrors, argument for argument, the arithmetic Ultralytics 8.3.176 does on the host around the
+kernels (the reference reaches it through ``model(frame)``, ``/root/reference/detect.py:541``):
+``LetterBox.__call__`` sizes and pads, ``ops.scale_boxes`` gain/pad, feature-map shapes per stride.
+Python ``round`` (half to even) and true division are part of the specification.
+"""
+
+from __future__ import annotations
+
+
+def letterbox_geometry(shape_hw, new_shape=(640, 640), auto=False, scale_fill=False, scaleup=True,
+                       center=True, stride=32):
+    """``ultralytics/data/augment.py::LetterBox.__call__`` geometry for one (h, w) source shape."""
+    h, w = int(shape_hw[0]), int(shape_hw[1])
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    r = min(new_shape[0] / h, new_shape[1] / w)
+    if not scaleup:
+        r = min(r, 1.0)
+    new_w, new_h = int(round(w * r)), int(round(h * r))
+    dw, dh = new_shape[1] - new_w, new_shape[0] - new_h
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    elif scale_fill:
+        dw, dh = 0.0, 0.0
+        new_w, new_h = new_shape[1], new_shape[0]
+    if center:
+        dw /= 2
+        dh /= 2
+    top, bottom = (int(round(dh - 0.1)) if center else 0), int(round(dh + 0.1))
+    left, right = (int(round(dw - 0.1)) if center else 0), int(round(dw + 0.1))
+    return dict(new_w=new_w, new_h=new_h, top=top, bottom=bottom, left=left, right=right,
+                out_h=new_h + top + bottom, out_w=new_w + left + right, ratio=r)
+
+
+def scale_boxes_params(img1_shape, img0_shape, ratio_pad=None):
+    """``ops.scale_boxes`` gain and (pad_x, pad_y) for letterboxed shape img1 -> source shape img0."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1),
+               round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    return gain, pad
+
+
+def level_shapes(in_h, in_w, strides=(8, 16, 32)):
+    """Detect-head feature-map (h, w) per stride for a letterboxed input (in_h, in_w)."""
+    return [(in_h // int(s), in_w // int(s)) for s in strides]
+
+
+def num_anchors(in_h, in_w, strides=(8, 16, 32)):
+    return sum(h * w for h, w in level_shapes(in_h, in_w, strides))
+
+
+def class_mask_words(classes, nc):
+    """Allow-list of class ids -> little-endian uint32 bit words (nc bits)."""
+    words = [0] * ((nc + 31) // 32)
+    for c in classes:
+        c = int(c)
+        if 0 <= c < nc:
+            words[c >> 5] |= 1 << (c & 31)
+    return words
+
+
+def shard_range(n_items, rank, world_size):
+    """Static block partition of frame indices: rank g of G takes [g*N/G, (g+1)*N/G)."""
+    return (rank * n_items) // world_size, ((rank + 1) * n_items) // world_size

@@ -1,0 +1,158 @@
+"""Whole hot path for a batch of frames: letterbox -> decode/filter -> sort -> NMS(+rescale) -> ROI crops.
+
+This is the batched, device-resident form of the reference's per-frame loop
+(``/root/reference/detect.py:535-600``): ``model(frame)`` (``detect.py:541``), the per-detection
+``int()`` + ``safe_crop(pad=6)`` (``detect.py:581-586``) and the per-crop ``rank_model(crop)``
+preprocessing (``detect.py:121``).  The backbone/neck stay torch modules outside this package: the
+Detect-head tensor is an input here (``head``), the letterboxed network input an output (``net_in``).
+
+All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 7 launches of
+this package's kernels plus two counter memsets, capturable into one CUDA graph.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import api, geometry
+
+RANK_CLASS_IDS = (6, 11, 16, 21, 26, 37, 43)  # *_rank classes, roadmap1.v3i.yolov8/data.yaml:6
+GPU_LAUNCHES_PER_STEP = 6                      # letterbox, decode_filter, sort, nms, select_rois, roi
+
+
+@dataclass
+class PipelineResult:
+    net_in: torch.Tensor        # (B,3,h,w) f32 letterboxed + normalised network input (K1)
+    det: api.Detections         # boxes in SOURCE pixels (scale_boxes fused into the NMS epilogue)
+    cand_count: torch.Tensor    # (B,) i32 candidates that passed conf (K2)
+    rois: torch.Tensor          # (roi_cap,3,S,S) f32 classifier batch (K5); first roi_count rows valid
+    roi_batch: torch.Tensor     # (roi_cap,) i32 frame index of each ROI
+    roi_det: torch.Tensor       # (roi_cap,) i32 detection row of each ROI
+    roi_valid: torch.Tensor     # (roi_cap,) i32
+    roi_count: torch.Tensor     # (1,) i32
+
+
+class Pipeline:
+    def __init__(self, batch: int, src_hw, nc: int, imgsz=640, auto=False, conf=0.25, iou=0.7, max_det=300,
+                 agnostic=False, classes=None, max_nms=30000, max_wh=7680, roi_classes: Sequence[int] = RANK_CLASS_IDS,
+                 rois_per_frame=8, pad=6, roi_size=64, strides=(8, 16, 32), device="cuda", cap=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("manual_yolo_b200.Pipeline needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.B, self.src_hw, self.nc = int(batch), (int(src_hw[0]), int(src_hw[1])), int(nc)
+        self.conf, self.iou, self.max_det, self.agnostic = conf, iou, max_det, agnostic
+        self.classes, self.max_nms, self.max_wh = classes, max_nms, max_wh
+        self.roi_classes, self.pad, self.roi_size, self.strides = tuple(roi_classes), pad, roi_size, tuple(strides)
+        new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        self.new_shape, self.auto = new_shape, auto
+        g = geometry.letterbox_geometry(self.src_hw, new_shape, auto=auto, stride=max(int(s) for s in strides))
+        self.geom = g
+        self.in_hw = (g["out_h"], g["out_w"])
+        self.level_hw = geometry.level_shapes(g["out_h"], g["out_w"], strides)
+        self.A = sum(h * w for h, w in self.level_hw)
+        self.cap = int(cap or self.A)
+        dev = self.device
+        B = self.B
+        self.net_in = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=dev)
+        self.cands = api.Candidates(torch.empty((B, self.cap, 6), dtype=torch.float32, device=dev),
+                                    torch.empty((B, self.cap), dtype=torch.int32, device=dev),
+                                    torch.zeros((B,), dtype=torch.int32, device=dev), self.cap)
+        self.ws = api.Workspace(B, self.cap, max_det, dev)
+        self.scale = api.scale_params_tensor(self.in_hw, [self.src_hw] * B, dev)
+        self.roi_cap = max(1, B * int(rois_per_frame))
+        self.roi_buf = (torch.empty((self.roi_cap, 4), dtype=torch.float32, device=dev),
+                        torch.empty((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.empty((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.zeros((1,), dtype=torch.int32, device=dev))
+        self.rois = torch.zeros((self.roi_cap, 3, roi_size, roi_size), dtype=torch.float32, device=dev)
+        self.roi_valid = torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev)
+        self._graph = None
+        self._static = None
+
+    # -- one step on device-resident inputs ------------------------------------------------------
+    def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
+        """frames: (B,H,W,3) uint8 BGR on the device; head: (B,64+nc,A) fp32 or list of level tensors."""
+        if tuple(frames.shape) != (self.B, self.src_hw[0], self.src_hw[1], 3):
+            raise ValueError(f"frames must be {(self.B, *self.src_hw, 3)}, got {tuple(frames.shape)}")
+        api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
+                       out=self.net_in)
+        api.decode_and_filter(head, self.strides, self.conf, self.classes, level_hw=self.level_hw,
+                              cap=self.cap, out=self.cands)
+        det = api.nms_candidates(self.cands, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
+                                 scale=self.scale, ws=self.ws)
+        api.select_rois(det, self.roi_classes, self.nc, self.roi_cap, out=self.roi_buf)
+        api.crop_resize_rois(frames, self.roi_buf[0], self.roi_buf[1], self.pad, self.roi_size,
+                             roi_count=self.roi_buf[3], out=self.rois, valid=self.roi_valid)
+        return PipelineResult(self.net_in, det, self.cands.count, self.rois, self.roi_buf[1], self.roi_buf[2],
+                              self.roi_valid, self.roi_buf[3])
+
+    # -- CUDA-graph form: one launch per batch ---------------------------------------------------
+    def capture(self, frames: torch.Tensor, head: torch.Tensor):
+        """Capture one step on static input buffers; afterwards ``replay()`` re-runs it (copy new data
+        into the tensors passed here first)."""
+        self._static = (frames, head)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self(frames, head)                       # warm-up: sets kernel attributes, touches buffers
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._result = self(frames, head)
+        return self._result
+
+    def replay(self) -> PipelineResult:
+        if self._graph is None:
+            raise RuntimeError("capture() first")
+        self._graph.replay()
+        return self._result
+
+    # -- host-facing entry: pinned host buffers in, host results out -----------------------------
+    def run_host(self, frames_host: torch.Tensor, head_host: torch.Tensor, staging=None):
+        """End-to-end call on HOST (pinned) buffers: H2D of the frames and the head tensor, the device
+        path, D2H of detections/counts.  Returns (det_rows, det_count, roi_count) host tensors."""
+        if staging is None:
+            staging = self.make_staging()
+        d_frames, d_head, h_rows, h_count, h_roi = staging
+        d_frames.copy_(frames_host, non_blocking=True)
+        d_head.copy_(head_host, non_blocking=True)
+        res = self(d_frames, d_head)
+        h_rows.copy_(res.det.rows, non_blocking=True)
+        h_count.copy_(res.det.count, non_blocking=True)
+        h_roi.copy_(res.roi_count, non_blocking=True)
+        return h_rows, h_count, h_roi
+
+    def make_staging(self):
+        dev = self.device
+        no = 64 + self.nc
+        return (torch.empty((self.B, self.src_hw[0], self.src_hw[1], 3), dtype=torch.uint8, device=dev),
+                torch.empty((self.B, no, self.A), dtype=torch.float32, device=dev),
+                torch.empty((self.B, self.max_det, 6), dtype=torch.float32).pin_memory(),
+                torch.empty((self.B,), dtype=torch.int32).pin_memory(),
+                torch.empty((1,), dtype=torch.int32).pin_memory())
+
+    def h2d_bytes_per_step(self):
+        return self.B * self.src_hw[0] * self.src_hw[1] * 3 + self.B * (64 + self.nc) * self.A * 4
+
+    def d2h_bytes_per_step(self):
+        return self.B * self.max_det * 6 * 4 + self.B * 4 + 4
+
+
+def detections_to_records(det_rows, det_count, names=None, frame_offset=0):
+    """Host-side gather into the reference's ``frame_data`` schema (``detect.py:590-598``), without the
+    OCR/tracker fields the path does not produce: bbox ints are ``int()``-truncated as ``detect.py:581``."""
+    recs = []
+    rows = det_rows.tolist() if hasattr(det_rows, "tolist") else det_rows
+    counts = det_count.tolist() if hasattr(det_count, "tolist") else det_count
+    for b, n in enumerate(counts):
+        for i in range(n):
+            x1, y1, x2, y2, conf, cls = rows[b][i]
+            cid = int(cls)
+            recs.append({"frame": frame_offset + b, "tracker_id": -1, "class_id": cid,
+                         "class_name": names.get(cid, f"class{cid}") if names else f"class{cid}",
+                         "bbox": [int(x1), int(y1), int(x2), int(y2)], "conf": round(float(conf), 3)})
+    return recs

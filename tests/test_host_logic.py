@@ -1,0 +1,87 @@
+"""Host-side logic of the product (no GPU): geometry mirrors, masks, sharding, record schema."""
+import numpy as np
+import pytest
+import torch
+
+from manual_yolo_b200 import geometry, pipeline, synth
+from oracle import boxes as oboxes
+from oracle import letterbox as olb
+
+
+@pytest.mark.parametrize("hw", [(1200, 1920), (900, 1600), (1130, 930), (543, 770), (1194, 1919), (1034, 1700),
+                                (64, 64), (100, 37), (2160, 3840)])
+@pytest.mark.parametrize("new", [640, 1280, (384, 640)])
+@pytest.mark.parametrize("auto", [False, True])
+def test_letterbox_geometry_matches_oracle(hw, new, auto):
+    a = geometry.letterbox_geometry(hw, new, auto=auto)
+    b = olb.letterbox_geometry(hw, new, auto=auto)
+    assert a == b
+
+
+def test_scale_params_and_levels():
+    gain, pad = geometry.scale_boxes_params((640, 640), (1200, 1920))
+    assert gain == 640 / 1920 and pad == (0, 120)
+    gain, pad = geometry.scale_boxes_params((384, 640), (900, 1600))
+    assert pad == (0, 12)
+    assert geometry.level_shapes(640, 640) == [(80, 80), (40, 40), (20, 20)]
+    assert geometry.num_anchors(640, 640) == 8400 and geometry.num_anchors(384, 640) == 5040
+    assert geometry.num_anchors(640, 544) == 7140 and geometry.num_anchors(928, 1280) == 24360
+
+
+def test_class_mask_and_shards():
+    assert geometry.class_mask_words([0, 31, 32, 63], 64) == [0x80000001, 0x80000001]
+    assert geometry.class_mask_words(pipeline.RANK_CLASS_IDS, 64) == [
+        sum(1 << c for c in pipeline.RANK_CLASS_IDS if c < 32), sum(1 << (c - 32) for c in pipeline.RANK_CLASS_IDS if c >= 32)]
+    spans = [geometry.shard_range(1000, r, 8) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == 1000
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
+    assert [b - a for a, b in spans] == [125] * 8
+    assert [geometry.shard_range(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+
+def test_detections_to_records_schema():
+    rows = torch.zeros((2, 3, 6))
+    rows[0, 0] = torch.tensor([10.9, 20.2, 30.7, 40.1, 0.87654, 6.0])
+    rows[1, 0] = torch.tensor([1.0, 2.0, 3.0, 4.0, 0.5, 63.0])
+    recs = pipeline.detections_to_records(rows, torch.tensor([1, 1]), names={6: "card1_rank"}, frame_offset=7)
+    assert recs[0] == {"frame": 7, "tracker_id": -1, "class_id": 6, "class_name": "card1_rank",
+                       "bbox": [10, 20, 30, 40], "conf": 0.877}
+    assert recs[1]["class_name"] == "class63" and recs[1]["frame"] == 8
+
+
+def test_synth_generators_are_seeded_and_guard_banded():
+    labels = synth.load_labels()
+    assert labels["boxes"].shape == (4259, 5) and labels["img_hw"].shape == (200, 2)
+    h1, gts = synth.synth_head_from_labels(2, 64, seed=3, labels=labels)
+    h2, _ = synth.synth_head_from_labels(2, 64, seed=3, labels=labels)
+    assert torch.equal(h1, h2) and h1.shape == (2, 128, 8400)
+    score = h1[:, 64:].max(1).values.sigmoid()
+    bits = score.view(torch.int32).long()
+    thr = int(torch.tensor([0.25]).view(torch.int32))
+    assert ((bits - thr).abs() > 16).all()
+    n = (score > 0.25).sum(1)
+    assert (n > 5).all() and (n < 400).all()
+    d = synth.synth_head_dense(1, 80, seed=0)
+    assert d.shape == (1, 144, 8400)
+    assert (d[:, 64:].max(1).values.sigmoid() > 0.001).float().mean() > 0.99
+    boxes, bidx = synth.synth_rois(256, 8, seed=0)
+    assert boxes.shape == (256, 4) and bidx.max() < 8
+    crops = [oboxes.safe_crop_box_ref((1200, 1920), *[int(v) for v in b]) for b in boxes]
+    assert all(c is not None for c in crops)
+
+
+def test_decoded_synthetic_head_round_trips_to_labels():
+    """Label-derived heads decode (through the oracle) back to the ground-truth boxes within ~1.5 px."""
+    from oracle import head as ohead
+    from oracle import nms as onms
+    labels = synth.load_labels()
+    head, gts = synth.synth_head_from_labels(2, 64, seed=5, labels=labels)
+    pred = ohead.detect_inference_ref(head, geometry.level_shapes(640, 640))
+    out = onms.non_max_suppression_ref(pred, 0.25, 0.7)
+    for o, gt in zip(out, gts):
+        assert 0.6 * len(gt) <= o.shape[0] <= 1.5 * len(gt) + 5
+        # every detection sits on a ground-truth box of its class
+        for row in o[:10]:
+            same = gt[gt[:, 4] == float(row[5])]
+            assert same.shape[0] > 0
+            assert np.abs(same[:, :4] - row[:4].numpy()).max(1).min() < 3.0
