@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- post-processed frames/s of the detection hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 16 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the whole path (letterbox -> decode/filter -> sort -> NMS+rescale -> ROI crops)
+over one batch of 64 synthetic 1920x1200 BGR frames + the matching (64,128,8400) Detect-head tensor
+(BASELINE.json configs[1]; the detector weights are absent from the reference, so the head is the
+label-derived synthetic one of manual_yolo_b200/synth.py).  Frames shard across ranks with no
+data-path collective (weak scaling: every rank runs its own 64-frame batches).
+
+One JSON line on stdout (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
+metric through Pipeline/HostRunner with pinned HOST buffers (H2D of frames + head and D2H of the
+detections inside the timed region); `roofline` = the dominant kernel (K1 letterbox) against the
+measured HBM peak; `cpu_baseline` = the oracle port timed on this box's host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "post-processed frames/sec"
+UNIT = "frames/s"
+BATCH, SRC_HW, NC, IMGSZ = 64, (1200, 1920), 64, 640
+CONF, IOU, MAX_DET = 0.25, 0.45, 300
+WORKLOAD = ("configs[1]: synthetic 1920x1200 BGR frames, batch=64, 8400 anchors, nc=64 poker head "
+            "(label-derived synthetic, poker_model.pt absent), conf=0.25 iou=0.45 max_det=300, "
+            "letterbox+decode+sort+NMS+scale_boxes+ROI crops 64x64")
+
+
+def _config(n_gpus, extra=None):
+    c = {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "frame_hw": list(SRC_HW),
+         "anchors": 8400, "nc": NC, "conf": CONF, "iou": IOU, "max_det": MAX_DET,
+         "parallelism": f"frame-sharded x{n_gpus}, no collective",
+         "l2_policy": "inputs larger than L2 (717 MB of frames+head per step vs 126 MB L2)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---- clocks sampled DURING the timed region -------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx = max(mx, float(p[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference's CPU path (oracle port) ---------------------------------------------------------
+def cpu_path_frames_per_s(frames, head, level_hw, in_hw, n_timed_batches=1, warm=True):
+    """Times the oracle (real cv2 / torch CPU / torchvision.ops.nms / PIL leaves + restated UL glue) on the
+    host cores over `frames` (numpy (n,H,W,3)) + `head` (torch (n,128,A))."""
+    import cv2
+    from oracle import boxes as oboxes
+    from oracle import head as ohead
+    from oracle import letterbox as olb
+    from oracle import nms as onms
+    from oracle import roi as oroi
+    from manual_yolo_b200.pipeline import RANK_CLASS_IDS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cv2.setNumThreads(cores)
+    H, W = frames.shape[1:3]
+
+    def one_pass():
+        olb.preprocess_ref(list(frames), (IMGSZ, IMGSZ))
+        pred = ohead.detect_inference_ref(head, level_hw)
+        out = onms.non_max_suppression_ref(pred, CONF, IOU, max_det=MAX_DET)
+        n_roi = 0
+        for b, o in enumerate(out):
+            o = o.clone()
+            o[:, :4] = oboxes.scale_boxes_ref(in_hw, o[:, :4], (H, W))
+            for row in o:
+                if int(row[5]) in RANK_CLASS_IDS:
+                    crop = oboxes.safe_crop_ref(frames[b], *[int(v) for v in row[:4]], pad=6)
+                    if crop is not None:
+                        oroi.classify_preprocess_ref(crop)
+                        n_roi += 1
+        return n_roi
+
+    if warm:
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(n_timed_batches):
+        one_pass()
+    dt = time.perf_counter() - t0
+    return frames.shape[0] * n_timed_batches / dt, cores, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (Ultralytics is not installable
+    here, so the oracle port is what runs), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from manual_yolo_b200 import geometry, synth
+    sample = 16                                  # frames per step: bounded sample of the 64-frame batch
+    in_hw = (IMGSZ, IMGSZ)
+    level_hw = geometry.level_shapes(*in_hw)
+    frames = synth.synth_frames(sample, *SRC_HW, seed=0).numpy()
+    head, _ = synth.synth_head_from_labels(sample, NC, in_hw=in_hw, src_hw=SRC_HW, seed=0, conf_thres=CONF)
+    for _ in range(max(1, args.warmup)):
+        cpu_path_frames_per_s(frames, head, level_hw, in_hw, 1, warm=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fps, cores, _ = cpu_path_frames_per_s(frames, head, level_hw, in_hw, 1, warm=False)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(args.gpus, {"sample_frames_per_step": sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} of the 64 frames of a step, {args.steps} steps, oracle port "
+                                       "(cv2/torch-CPU/torchvision.nms/PIL leaves), all host threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local):
+    import manual_yolo_b200 as m
+    from manual_yolo_b200 import multigpu, synth
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pipe = m.Pipeline(BATCH, SRC_HW, NC, imgsz=IMGSZ, conf=CONF, iou=IOU, max_det=MAX_DET, device=dev)
+
+    # inputs: seeded per rank (config 5: seeds = base + rank); generated on the CPU so the oracle sees the same bits
+    frames_h = synth.synth_frames(BATCH, *SRC_HW, seed=rank).pin_memory()
+    head_h, _ = synth.synth_head_from_labels(BATCH, NC, in_hw=pipe.in_hw, src_hw=SRC_HW, seed=rank, conf_thres=CONF)
+    head_h = head_h.pin_memory()
+    frames_d, head_d = frames_h.to(dev), head_h.to(dev)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps between barriers ----
+    for _ in range(max(3, args.warmup)):
+        res = pipe(frames_d, head_d)
+    torch.cuda.synchronize()
+    pipe.enable_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    multigpu.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        res = pipe(frames_d, head_d)
+    e1.record()
+    torch.cuda.synchronize()
+    multigpu.barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    ms_max = multigpu.max_over_ranks(ms, dev)
+    kt = pipe.kernel_times_ms()
+    pipe.enable_profiling(False)
+    total_frames = BATCH * args.steps * world
+    value = total_frames / (ms_max / 1e3)
+
+    # ---- end to end on host buffers (H2D frames+head, D2H detections, every step) ----
+    runner = m.HostRunner(pipe, depth=2)
+    for _ in range(2):
+        out = runner.submit(frames_h, head_h)
+    torch.cuda.synchronize()
+    multigpu.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = runner.submit(frames_h, head_h)
+    e1.record()
+    torch.cuda.synchronize()
+    multigpu.barrier()
+    e2e_ms = multigpu.max_over_ranks(e0.elapsed_time(e1), dev)
+    t2 = time.time()
+    clocks = sampler.stop(t0, t2) if rank == 0 else None
+    e2e_value = total_frames / (e2e_ms / 1e3)
+    n_det = int(out[1].sum())
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (K1 letterbox), algorithmic bytes per launch ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    g = pipe.geom
+    k1_bytes_frame = g["new_h"] * SRC_HW[1] * 3 + 3 * g["out_h"] * g["out_w"] * 4     # 7 219 200 B
+    k1_ms = statistics.mean(kt["letterbox"])
+    achieved = BATCH * k1_bytes_frame / (k1_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("letterbox_bytes_per_launch")
+    except Exception:
+        pass
+    kernels = {}
+    bytes_per_launch = {
+        "letterbox": BATCH * k1_bytes_frame,
+        "decode_filter": BATCH * (64 + NC) * pipe.A * 4,
+    }
+    for name, v in kt.items():
+        kernels[name] = {"us": 1e3 * statistics.mean(v)}
+        if name in bytes_per_launch:
+            kernels[name]["algo_GBps"] = bytes_per_launch[name] / (statistics.mean(v) / 1e3) / 1e9
+            kernels[name]["frac_of_measured_peak"] = kernels[name]["algo_GBps"] / peak
+    pipeline_bytes_frame = k1_bytes_frame + (64 + NC) * pipe.A * 4 + 10_000 + 4 * 60_000
+    # ---- CPU baseline (oracle port) on a bounded sample of the same workload ----
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        n = 16
+        fps, cores, dt = cpu_path_frames_per_s(frames_h[:n].numpy(), head_h[:n].clone(), pipe.level_hw, pipe.in_hw, 2)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n} frames of the rank-0 batch, 1 warm-up + 2 timed passes ({dt:.1f} s), oracle port "
+                         "(cv2 / torch CPU / torchvision.ops.nms / PIL), torch+cv2 threads = all cores"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(),
+                    "d2h_bytes_per_step": pipe.d2h_bytes_per_step(), "ms_per_step": e2e_ms / args.steps,
+                    "note": "HostRunner: pinned host frames+head -> device path -> detections back, double-buffered"},
+            "gpu_launches": m.pipeline.GPU_LAUNCHES_PER_STEP * args.steps * world,
+            "roofline": {"kernel": "letterbox_kernel<float> (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": BATCH * k1_bytes_frame, "avg_launch_us": 1e3 * k1_ms},
+            "kernels": kernels,
+            "pipeline_roofline": {"bytes_per_frame": pipeline_bytes_frame,
+                                  "roofline_frames_per_s_per_gpu": peak * 1e9 / pipeline_bytes_frame,
+                                  "frac": (value / world) / (peak * 1e9 / pipeline_bytes_frame)},
+            "cpu_baseline": cpu, "clocks": clocks, "detections_last_step": n_det}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    from manual_yolo_b200 import multigpu
+    rank, world, local = multigpu.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    try:
+        run_ours(args, rank, world, local)
+    finally:
+        if torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

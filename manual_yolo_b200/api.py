@@ -229,21 +229,30 @@ def sort_candidates(cands: Candidates, max_nms=30000, ws: Optional[Workspace] = 
     return ws
 
 
-def nms_candidates(cands: Candidates, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680,
-                   scale: Optional[torch.Tensor] = None, ws: Optional[Workspace] = None) -> Detections:
-    """K3 + K4 on K2's candidates.  ``scale``: optional (B,5) f32 {gain,pad_x,pad_y,w0,h0} -> source pixels."""
+def nms_sorted(cands: Candidates, ws: Workspace, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000,
+               max_wh=7680, scale: Optional[torch.Tensor] = None) -> Detections:
+    """K4 on candidates whose order array (``ws.order``) was filled by ``sort_candidates``."""
     if not 0 <= iou_thres <= 1:
         raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
     B = cands.rows.shape[0]
-    if ws is None or ws.max_det != max_det or ws.cap != cands.cap or ws.B != B:
-        ws = Workspace(B, cands.cap, max_det, cands.rows.device)
-    sort_candidates(cands, max_nms, ws)
+    if ws.max_det != max_det or ws.cap != cands.cap or ws.B != B:
+        raise ValueError("workspace does not match (B, cap, max_det)")
     rc = _lib.load().b200yolo_nms(_ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), _ptr(ws.order), B,
                                   cands.cap, int(max_nms), float(iou_thres), float(max_wh), int(bool(agnostic)),
                                   int(max_det), _ptr(scale), _ptr(ws.det.rows), _ptr(ws.det.anchor),
                                   _ptr(ws.det.count), _ptr(ws.ws), ws.ws.numel(), _stream())
-    _lib.check(rc, "nms_candidates")
+    _lib.check(rc, "nms")
     return ws.det
+
+
+def nms_candidates(cands: Candidates, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680,
+                   scale: Optional[torch.Tensor] = None, ws: Optional[Workspace] = None) -> Detections:
+    """K3 + K4 on K2's candidates.  ``scale``: optional (B,5) f32 {gain,pad_x,pad_y,w0,h0} -> source pixels."""
+    B = cands.rows.shape[0]
+    if ws is None or ws.max_det != max_det or ws.cap != cands.cap or ws.B != B:
+        ws = Workspace(B, cands.cap, max_det, cands.rows.device)
+    sort_candidates(cands, max_nms, ws)
+    return nms_sorted(cands, ws, iou_thres, agnostic, max_det, max_nms, max_wh, scale)
 
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,

@@ -178,7 +178,7 @@ int launch_letterbox(const uint8_t* src, int B, int H, int W, int64_t pitch, int
   B200_REQUIRE(src && dst, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0 && new_w > 0 && new_h > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(top >= 0 && left >= 0 && top + new_h <= outH && left + new_w <= outW, B200YOLO_ERR_SHAPE);
-  B200_REQUIRE(pitch >= (int64_t)W * 3 && bstride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || bstride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
   B200_REQUIRE(pad_value >= 0 && pad_value <= 255, B200YOLO_ERR_RANGE);
   B200_REQUIRE(B <= 65535 && outH <= 2147483647, B200YOLO_ERR_UNSUPPORTED);
   LbParams p;

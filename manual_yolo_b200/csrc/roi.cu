@@ -235,7 +235,7 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
                                         void* stream) {
   B200_REQUIRE(frames && boxes && batch_idx && dst && valid, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && N >= 0 && pad >= 0, B200YOLO_ERR_SHAPE);
-  B200_REQUIRE(pitch >= (int64_t)W * 3 && batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
   B200_REQUIRE(size > 0 && size <= kMaxSize, B200YOLO_ERR_UNSUPPORTED);
   if (N == 0) return B200YOLO_OK;
   const size_t smem = 2 * sizeof(AxisPlan) + (size_t)kRowsMax * kMaxSize * 3;

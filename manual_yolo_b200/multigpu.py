@@ -1,0 +1,76 @@
+"""Frame sharding across the GPUs of one box: one process per GPU, static block
+partition of the frame stream, NO data-path collective.  ``torch.distributed`` is used only for the
+rendezvous, the timing barrier / max-over-ranks reduction and the final host-side gather of the
+per-frame detection records (the reference writes them as JSON, ``/root/reference/detect.py:679-690``).
+"""
+
+from __future__ import annotations
+
+import os
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import geometry
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise the default process group from torchrun's env (RANK/WORLD_SIZE/MASTER_*).
+    Returns (rank, world_size, local_rank).  Single-process runs need no group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def my_frames(n_frames: int, rank: int, world: int):
+    """Frame index range [lo, hi) this rank processes."""
+    return geometry.shard_range(n_frames, rank, world)
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Max of a per-rank scalar (elapsed device time) over the job."""
+    if not dist.is_initialized():
+        return float(value)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not dist.is_initialized():
+        return float(value)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_records(records: List[dict], dst: int = 0):
+    """Host-side gather of per-frame detection records to rank ``dst`` (sorted by frame index).
+    Returns the merged list on ``dst`` and None elsewhere."""
+    if not dist.is_initialized():
+        return sorted(records, key=lambda r: r["frame"])
+    world = dist.get_world_size()
+    out = [None] * world if dist.get_rank() == dst else None
+    dist.gather_object(records, out, dst=dst)
+    if dist.get_rank() != dst:
+        return None
+    merged = [r for part in out for r in part]
+    merged.sort(key=lambda r: r["frame"])
+    return merged

@@ -71,23 +71,55 @@ class Pipeline:
         self.roi_valid = torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev)
         self._graph = None
         self._static = None
+        self._prof = None
+        self._open = None
 
     # -- one step on device-resident inputs ------------------------------------------------------
     def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
         """frames: (B,H,W,3) uint8 BGR on the device; head: (B,64+nc,A) fp32 or list of level tensors."""
         if tuple(frames.shape) != (self.B, self.src_hw[0], self.src_hw[1], 3):
             raise ValueError(f"frames must be {(self.B, *self.src_hw, 3)}, got {tuple(frames.shape)}")
+        t = self._tick
+        t("letterbox")
         api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
                        out=self.net_in)
+        t("decode_filter")
         api.decode_and_filter(head, self.strides, self.conf, self.classes, level_hw=self.level_hw,
                               cap=self.cap, out=self.cands)
-        det = api.nms_candidates(self.cands, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
-                                 scale=self.scale, ws=self.ws)
+        t("sort_topk")
+        api.sort_candidates(self.cands, self.max_nms, self.ws)
+        t("nms")
+        det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
+                             scale=self.scale)
+        t("select_rois")
         api.select_rois(det, self.roi_classes, self.nc, self.roi_cap, out=self.roi_buf)
+        t("roi_crop_resize")
         api.crop_resize_rois(frames, self.roi_buf[0], self.roi_buf[1], self.pad, self.roi_size,
                              roi_count=self.roi_buf[3], out=self.rois, valid=self.roi_valid)
+        t(None)
         return PipelineResult(self.net_in, det, self.cands.count, self.rois, self.roi_buf[1], self.roi_buf[2],
                               self.roi_valid, self.roi_buf[3])
+
+    # -- per-kernel CUDA-event timing (bench.py): events on the launching stream around each stage --
+    def enable_profiling(self, on=True):
+        self._prof = [] if on else None
+        self._open = None
+
+    def _tick(self, name):
+        if getattr(self, "_prof", None) is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if self._open is not None:
+            self._prof.append((self._open[0], self._open[1], ev))
+        self._open = (name, ev) if name is not None else None
+
+    def kernel_times_ms(self):
+        """{stage: [ms per recorded launch]} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for name, a, b in self._prof or []:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
 
     # -- CUDA-graph form: one launch per batch ---------------------------------------------------
     def capture(self, frames: torch.Tensor, head: torch.Tensor):
@@ -140,6 +172,40 @@ class Pipeline:
 
     def d2h_bytes_per_step(self):
         return self.B * self.max_det * 6 * 4 + self.B * 4 + 4
+
+
+class HostRunner:
+    """End-to-end driver on HOST buffers: every step copies that step's frames + head tensor from pinned
+    host memory (copy stream), runs the device path (compute stream) and reads the detections back.
+    Two staging sets let step i+1's H2D overlap step i's kernels."""
+
+    def __init__(self, pipe: Pipeline, depth=2):
+        self.pipe, self.depth = pipe, depth
+        self.staging = [pipe.make_staging() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=pipe.device)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.step = 0
+
+    def submit(self, frames_host: torch.Tensor, head_host: torch.Tensor):
+        """Enqueue one step; returns the (rows, count, roi_count) pinned host tensors it will fill."""
+        s = self.step % self.depth
+        d_frames, d_head, h_rows, h_count, h_roi = self.staging[s]
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if self.step >= self.depth:
+                self.copy_stream.wait_event(self.free[s])
+            d_frames.copy_(frames_host, non_blocking=True)
+            d_head.copy_(head_host, non_blocking=True)
+            self.ready[s].record(self.copy_stream)
+        compute.wait_event(self.ready[s])
+        res = self.pipe(d_frames, d_head)
+        h_rows.copy_(res.det.rows, non_blocking=True)
+        h_count.copy_(res.det.count, non_blocking=True)
+        h_roi.copy_(res.roi_count, non_blocking=True)
+        self.free[s].record(compute)
+        self.step += 1
+        return h_rows, h_count, h_roi
 
 
 def detections_to_records(det_rows, det_count, names=None, frame_offset=0):

@@ -1,0 +1,110 @@
+"""K2 parity (rows a3-a7): CUDA decode+filter vs the torch-CPU oracle on identical seeded heads."""
+import numpy as np
+import pytest
+import torch
+
+import manual_yolo_b200 as m
+from manual_yolo_b200 import geometry, synth
+from oracle import head as ohead
+from oracle import nms as onms
+
+pytestmark = pytest.mark.gpu
+
+BOX_TOL = 1e-4     # north_star: boxes and scores within 1e-4 absolute in fp32
+SCORE_TOL = 1e-4
+
+
+def _compare(head, level_hw, conf, cuda_dev, classes=None, levels=None):
+    pred = ohead.detect_inference_ref(head, level_hw)
+    ref = onms.filter_candidates_ref(pred, conf, classes)
+    src = [x.to(cuda_dev) for x in levels] if levels is not None else head.to(cuda_dev)
+    c = m.decode_and_filter(src, conf_thres=conf, classes=classes, level_hw=level_hw)
+    counts = c.count.cpu().tolist()
+    stats = dict(n=0, box_max=0.0, score_max=0.0, score_bit_equal=0, box_bit_equal=0)
+    for b, (rows_ref, idx_ref) in enumerate(ref):
+        n = counts[b]
+        rows = c.rows[b, :n].cpu()
+        anchor = c.anchor[b, :n].cpu().long()
+        order = anchor.argsort()
+        rows, anchor = rows[order], anchor[order]
+        assert torch.equal(anchor, idx_ref), f"image {b}: candidate set differs"
+        assert torch.equal(rows[:, 5], rows_ref[:, 5]), "class ids differ"
+        if n:
+            stats["box_max"] = max(stats["box_max"], (rows[:, :4] - rows_ref[:, :4]).abs().max().item())
+            stats["score_max"] = max(stats["score_max"], (rows[:, 4] - rows_ref[:, 4]).abs().max().item())
+            stats["score_bit_equal"] += int((rows[:, 4] == rows_ref[:, 4]).sum())
+            stats["box_bit_equal"] += int((rows[:, :4] == rows_ref[:, :4]).all(1).sum())
+        stats["n"] += n
+    assert stats["box_max"] <= BOX_TOL and stats["score_max"] <= SCORE_TOL, stats
+    return stats
+
+
+@pytest.mark.parametrize("in_hw,src_hw", [((640, 640), (1200, 1920)), ((384, 640), (900, 1600)),
+                                          ((640, 544), (1130, 930))])
+def test_label_derived_head(cuda_dev, in_hw, src_hw):
+    head, _ = synth.synth_head_from_labels(4, 64, in_hw=in_hw, src_hw=src_hw, seed=0, conf_thres=0.25)
+    lv = geometry.level_shapes(*in_hw)
+    st = _compare(head, lv, 0.25, cuda_dev)
+    assert st["n"] > 100
+    # expf_torch restates torch's Sleef expf: decode is expected bit-identical, not merely within 1e-4
+    assert st["score_bit_equal"] >= 0.999 * st["n"] and st["box_bit_equal"] >= 0.999 * st["n"], st
+
+
+def test_dense_eval_regime(cuda_dev):
+    """Config-3 shape at small batch: nc=80, conf=0.001, ~every anchor is a candidate."""
+    head = synth.synth_head_dense(2, 80, seed=0)
+    st = _compare(head, geometry.level_shapes(640, 640), 0.001, cuda_dev)
+    assert st["n"] > 2 * 8000
+    assert st["box_bit_equal"] >= 0.999 * st["n"], st
+
+
+def test_per_level_tensors_equal_concatenated(cuda_dev):
+    head, _ = synth.synth_head_from_labels(2, 64, seed=2)
+    lv = geometry.level_shapes(640, 640)
+    levels, off = [], 0
+    for h, w in lv:
+        levels.append(head[:, :, off:off + h * w].reshape(2, 128, h, w).contiguous())
+        off += h * w
+    assert torch.equal(ohead.cat_levels(levels), head)
+    _compare(head, lv, 0.25, cuda_dev, levels=levels)
+
+
+def test_classes_filter_and_class_tie_lowest_index(cuda_dev):
+    head, _ = synth.synth_head_from_labels(2, 64, seed=4)
+    lv = geometry.level_shapes(640, 640)
+    _compare(head, lv, 0.25, cuda_dev, classes=[6, 11, 16, 40, 63])
+    # saturated / tied class logits: cls.max(1) returns the LOWEST index among equal sigmoids
+    h2 = head.clone()
+    h2[:, 64:, 100] = -8.0
+    h2[:, 64 + 9, 100] = 30.0       # sigmoid == 1.0f
+    h2[:, 64 + 3, 100] = 25.0       # also rounds to 1.0f, lower index, smaller logit
+    h2[:, 64 + 20, 101] = 2.0
+    h2[:, 64 + 7, 101] = 2.0        # exact logit tie
+    st = _compare(h2, lv, 0.25, cuda_dev)
+    c = m.decode_and_filter(h2.to(cuda_dev), conf_thres=0.25, level_hw=lv)
+    rows, anchor = c.rows[0, :int(c.count[0])].cpu(), c.anchor[0, :int(c.count[0])].cpu()
+    assert rows[anchor == 100][0, 5] == 3.0 and rows[anchor == 101][0, 5] == 7.0
+    assert st["n"] > 0
+
+
+def test_empty_and_overflow(cuda_dev):
+    lv = geometry.level_shapes(64, 64)
+    A = sum(h * w for h, w in lv)
+    head = torch.full((1, 128, A), -20.0)
+    c = m.decode_and_filter(head.to(cuda_dev), conf_thres=0.25, level_hw=lv)
+    assert int(c.count[0]) == 0
+    head[:, 64:, :] = 3.0
+    c = m.decode_and_filter(head.to(cuda_dev), conf_thres=0.25, level_hw=lv, cap=10)
+    assert int(c.count[0]) == A     # count keeps growing past cap so the host can see the overflow
+
+
+def test_filter_decoded_matches_oracle(cuda_dev):
+    head = synth.synth_head_dense(2, 80, seed=3)
+    pred = ohead.detect_inference_ref(head, geometry.level_shapes(640, 640))
+    ref = onms.filter_candidates_ref(pred, 0.3)
+    c = m.filter_decoded(pred.to(cuda_dev), 0.3)
+    for b, (rows_ref, idx_ref) in enumerate(ref):
+        n = int(c.count[b])
+        order = c.anchor[b, :n].cpu().long().argsort()
+        assert torch.equal(c.anchor[b, :n].cpu().long()[order], idx_ref)
+        assert torch.equal(c.rows[b, :n].cpu()[order], rows_ref)   # bit-exact: identical score bits in

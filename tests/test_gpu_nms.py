@@ -1,0 +1,136 @@
+"""K3/K4 parity (rows a8-a10): kept anchor indices, class ids and rows BIT-EXACT against the oracle
+(real torchvision.ops.nms) on identical score bits."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+import manual_yolo_b200 as m
+from manual_yolo_b200 import geometry, synth
+from oracle import boxes as oboxes
+from oracle import head as ohead
+from oracle import nms as onms
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(pred, cuda_dev, **kw):
+    ref_out, ref_idx = onms.non_max_suppression_ref(pred, return_idxs=True, **kw)
+    out, idx = m.non_max_suppression(pred.to(cuda_dev), return_idxs=True, **kw)
+    assert len(out) == len(ref_out)
+    kept = 0
+    for o, i, ro, ri in zip(out, idx, ref_out, ref_idx):
+        assert torch.equal(i.cpu(), ri), "kept anchor indices differ"
+        assert torch.equal(o.cpu(), ro), "kept rows differ"
+        kept += len(ri)
+    return kept
+
+
+@pytest.mark.parametrize("iou", [0.45, 0.5, 0.6, 0.7])
+def test_dense_eval_regime_bit_exact(cuda_dev, iou):
+    """n ~ 8400 candidates/image, nc=80, adversarial ties / degenerate boxes / class-79 offsets (config 3)."""
+    head = synth.synth_head_dense(3, 80, seed=int(iou * 100))
+    pred = ohead.detect_inference_ref(head, geometry.level_shapes(640, 640))
+    kept = _check(pred, cuda_dev, conf_thres=0.001, iou_thres=iou, max_det=300)
+    assert kept == 3 * 300
+
+
+@pytest.mark.parametrize("conf,iou", [(0.25, 0.45), (0.25, 0.7), (0.5, 0.7), (0.35, 0.7)])
+def test_label_derived_bit_exact(cuda_dev, conf, iou):
+    head, _ = synth.synth_head_from_labels(6, 64, seed=1, conf_thres=conf)
+    pred = ohead.detect_inference_ref(head, geometry.level_shapes(640, 640))
+    assert _check(pred, cuda_dev, conf_thres=conf, iou_thres=iou) > 50
+
+
+def test_options_max_det_agnostic_classes_max_nms(cuda_dev):
+    head = synth.synth_head_dense(2, 80, seed=9)
+    pred = ohead.detect_inference_ref(head, geometry.level_shapes(640, 640))
+    _check(pred, cuda_dev, conf_thres=0.01, iou_thres=0.7, max_det=17)
+    _check(pred, cuda_dev, conf_thres=0.01, iou_thres=0.5, agnostic=True, max_det=1000)
+    _check(pred, cuda_dev, conf_thres=0.001, iou_thres=0.7, classes=[0, 5, 79])
+    _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.7, max_det=3000)      # no early exit: full sweep
+    # n > max_nms keeps the top max_nms scores (ties at the cut are unspecified upstream: none here)
+    _check(pred, cuda_dev, conf_thres=0.001, iou_thres=0.7, max_nms=1000)
+
+
+def test_medium_sizes_cover_enumeration_and_radix_paths(cuda_dev):
+    g = torch.Generator().manual_seed(5)
+    for n_obj in (1, 40, 511, 512, 513, 700, 1500, 4000):
+        A = 8400
+        pred = torch.zeros((1, 4 + 16, A))
+        pred[0, 0] = torch.rand(A, generator=g) * 600
+        pred[0, 1] = torch.rand(A, generator=g) * 600
+        pred[0, 2] = torch.rand(A, generator=g) * 90 + 5
+        pred[0, 3] = torch.rand(A, generator=g) * 90 + 5
+        sel = torch.randperm(A, generator=g)[:n_obj]
+        pred[0, 4 + torch.randint(0, 16, (n_obj,), generator=g), sel] = torch.rand(n_obj, generator=g) * 0.7 + 0.3
+        _check(pred, cuda_dev, conf_thres=0.25, iou_thres=0.45, max_det=300)
+
+
+def test_ties_duplicates_degenerates(cuda_dev):
+    A = 64
+    pred = torch.zeros((2, 4 + 3, A))
+    # image 0: identical boxes with identical scores (stable tie -> lower anchor kept), duplicates in
+    # other classes survive, zero-area twins both survive (0/0 = NaN never suppresses)
+    pred[0, :4, 5] = torch.tensor([100., 100., 50., 50.]); pred[0, 4, 5] = 0.9
+    pred[0, :4, 9] = torch.tensor([100., 100., 50., 50.]); pred[0, 4, 9] = 0.9
+    pred[0, :4, 2] = torch.tensor([100., 100., 50., 50.]); pred[0, 5, 2] = 0.9
+    pred[0, :4, 20] = torch.tensor([300., 300., 0., 0.]); pred[0, 6, 20] = 0.8
+    pred[0, :4, 21] = torch.tensor([300., 300., 0., 0.]); pred[0, 6, 21] = 0.8
+    # IoU exactly float32(0.6): suppressed at iou_thres=0.6 (double compare), kept at float32(0.6)
+    pred[1, :4, 0] = torch.tensor([2.5, 0.5, 5., 1.]); pred[1, 4, 0] = 0.9
+    pred[1, :4, 1] = torch.tensor([1.5, 0.5, 3., 1.]); pred[1, 4, 1] = 0.8
+    out = m.non_max_suppression(pred.to(cuda_dev), 0.25, 0.45, return_idxs=True)
+    assert out[1][0].cpu().tolist() == [2, 5, 20, 21]
+    _check(pred, cuda_dev, conf_thres=0.25, iou_thres=0.45)
+    _check(pred, cuda_dev, conf_thres=0.25, iou_thres=0.6)
+    _check(pred, cuda_dev, conf_thres=0.25, iou_thres=float(np.float32(0.6)))
+    a = m.non_max_suppression(pred.to(cuda_dev), 0.25, 0.6)[1]
+    b = m.non_max_suppression(pred.to(cuda_dev), 0.25, float(np.float32(0.6)))[1]
+    assert a.shape[0] == 1 and b.shape[0] == 2
+
+
+def test_empty_images_and_ragged_batch(cuda_dev):
+    pred = torch.zeros((3, 4 + 5, 100))
+    pred[1, :4, 7] = torch.tensor([50., 50., 20., 20.]); pred[1, 6, 7] = 0.6
+    out = m.non_max_suppression(pred.to(cuda_dev), 0.25, 0.45)
+    assert [o.shape for o in out] == [(0, 6), (1, 6), (0, 6)]
+    _check(pred, cuda_dev, conf_thres=0.25, iou_thres=0.45)
+
+
+def test_torchvision_golden(cuda_dev, golden_dir):
+    """Kept indices recorded from torchvision.ops.nms in the dev container (tests/golden/nms_golden.npz)."""
+    z = np.load(os.path.join(golden_dir, "nms_golden.npz"))
+    for t in range(4):
+        b, s, c, thr = z[f"boxes{t}"], z[f"scores{t}"], z[f"cls{t}"], float(z[f"thr{t}"])
+        n, nc = len(s), int(c.max()) + 1
+        rows = torch.zeros((1, n, 6))
+        rows[0, :, :4] = torch.from_numpy(b); rows[0, :, 4] = torch.from_numpy(s); rows[0, :, 5] = torch.from_numpy(c)
+        cands = m.Candidates(rows.to(cuda_dev), torch.arange(n, dtype=torch.int32, device=cuda_dev)[None].contiguous(),
+                             torch.tensor([n], dtype=torch.int32, device=cuda_dev), n)
+        det = m.nms_candidates(cands, thr, max_det=4096)
+        k = int(det.count[0])
+        assert np.array_equal(det.anchor[0, :k].cpu().numpy(), z[f"keep{t}"][:4096])
+
+
+def test_scale_boxes_bit_exact(cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    for img1, img0 in [((640, 640), (1200, 1920)), ((384, 640), (900, 1600)), ((640, 544), (1130, 930)),
+                       ((928, 1280), (543, 770))]:
+        b = torch.rand((500, 6), generator=g) * 700 - 30
+        ref = oboxes.scale_boxes_ref(img1, b[:, :4], img0)
+        got = m.scale_boxes(img1, b.clone().to(cuda_dev), img0)
+        assert torch.equal(got[:, :4].cpu(), ref) and torch.equal(got[:, 4:].cpu(), b[:, 4:])
+    # fused form inside the NMS epilogue
+    head, _ = synth.synth_head_from_labels(2, 64, seed=8)
+    pred = ohead.detect_inference_ref(head, geometry.level_shapes(640, 640))
+    ref = onms.non_max_suppression_ref(pred, 0.25, 0.7)
+    cands = m.filter_decoded(pred.to(cuda_dev), 0.25)
+    scale = m.scale_params_tensor((640, 640), [(1200, 1920)] * 2, cuda_dev)
+    det = m.nms_candidates(cands, 0.7, scale=scale)
+    for bi in range(2):
+        exp = ref[bi].clone()
+        exp[:, :4] = oboxes.scale_boxes_ref((640, 640), exp[:, :4], (1200, 1920))
+        assert torch.equal(det.rows[bi, :int(det.count[bi])].cpu(), exp)

@@ -1,0 +1,112 @@
+"""K5 parity (rows a12-a14): ROI crop + Pillow-exact resize vs the real PIL/torchvision oracle; the
+classifier known answer (63/67) through the CUDA path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import manual_yolo_b200 as m
+from manual_yolo_b200 import synth
+from oracle import boxes as oboxes
+from oracle import classifier as ocls
+from oracle import roi as oroi
+
+pytestmark = pytest.mark.gpu
+ROI_TOL = 1.0 / 255.0      # north_star: ROI tensors within 1/255 (the kernel targets 0)
+
+
+def _kat_crops(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rank_classifier_kat.npz"))
+    hw, flat = z["crop_hw"], z["crops"]
+    offs = np.concatenate([[0], np.cumsum(hw[:, 0] * hw[:, 1] * 3)])
+    return z, [flat[offs[i]:offs[i + 1]].reshape(h, w, 3) for i, (h, w) in enumerate(hw)]
+
+
+def test_kat_crops_bit_exact_and_chain_63_of_67(cuda_dev, golden_dir):
+    z, crops = _kat_crops(golden_dir)
+    # paste the 67 validation crops on a canvas; boxes address them exactly (pad=0)
+    H, W = 512, 1024
+    canvas = np.random.default_rng(0).integers(0, 256, (1, H, W, 3), dtype=np.uint8)
+    boxes, x, y, rowh = [], 4, 4, 0
+    for c in crops:
+        h, w = c.shape[:2]
+        if x + w + 4 > W:
+            x, y, rowh = 4, y + rowh + 4, 0
+        canvas[0, y:y + h, x:x + w] = c
+        boxes.append([x + 0.25, y + 0.75, x + w + 0.5, y + h + 0.99])   # int() truncation on device
+        x, rowh = x + w + 4, max(rowh, h)
+    boxes = torch.tensor(boxes, dtype=torch.float32, device=cuda_dev)
+    bidx = torch.zeros((len(crops),), dtype=torch.int32, device=cuda_dev)
+    out, valid = m.crop_resize_rois(torch.from_numpy(canvas).to(cuda_dev), boxes, bidx, pad=0)
+    assert valid.cpu().tolist() == [1] * len(crops)
+    got_u8 = (out * 255).round().to(torch.uint8).cpu().numpy()
+    assert np.array_equal(got_u8, z["roi_u8"])                               # == real PIL, recorded
+    assert torch.equal(out.cpu(), torch.from_numpy(z["roi_u8"]).float().div(255))
+    # chain: K5 batch -> YOLOv8n-cls (torch, on the GPU) -> the reference's known answer
+    sd = ocls.state_dict_from_npz(z, device=cuda_dev)
+    logits = ocls.forward_logits(sd, out)
+    labels = torch.from_numpy(z["labels"]).long().to(cuda_dev)
+    assert int((logits.argmax(1) == labels).sum()) == 63
+    assert int((logits.topk(5, 1).indices == labels[:, None]).any(1).sum()) == 66
+    assert torch.equal(logits.argmax(1).cpu(), torch.from_numpy(z["logits"]).argmax(1))
+
+
+def test_synthetic_rois_vs_pil_oracle(cuda_dev):
+    """Config-4 distribution: up- and down-scaling, borders, safe_crop(pad=6) clamping."""
+    B, N = 4, 768
+    frames = synth.synth_frames(B, 1200, 1920, seed=2)
+    boxes, bidx = synth.synth_rois(N, B, seed=0)
+    out, valid = m.crop_resize_rois(frames.to(cuda_dev), boxes.to(cuda_dev), bidx.to(cuda_dev), pad=6)
+    out, valid = out.cpu(), valid.cpu()
+    worst, exact = 0.0, 0
+    for i in range(N):
+        crop = oboxes.safe_crop_ref(frames[bidx[i]].numpy(), *[int(v) for v in boxes[i]], pad=6)
+        assert crop is not None and valid[i] == 1
+        ref = oroi.classify_preprocess_ref(crop)
+        d = (out[i] - ref).abs().max().item()
+        worst, exact = max(worst, d), exact + (d == 0.0)
+    assert worst <= ROI_TOL, worst
+    assert exact == N, f"{exact}/{N} bit-exact, worst {worst}"
+
+
+def test_invalid_border_and_large_rois(cuda_dev):
+    frames = synth.synth_frames(1, 400, 600, seed=4)
+    boxes = torch.tensor([[700., 10., 720., 40.],      # right of the frame: x1 clamps to w-1, x2 to w -> 1 px wide
+                          [50., 50., 40., 90.],         # x2 < x1 beyond the padding -> None
+                          [-20., -20., 30., 30.],       # top-left corner
+                          [0., 0., 600., 400.],         # whole frame: strong antialias (scale 6.25)
+                          [590., 390., 605., 405.],     # bottom-right corner
+                          [100., 100., 164., 164.]])    # exactly 64+12 -> mild down-scale
+    boxes[1, 2] = 30.0
+    bidx = torch.zeros((6,), dtype=torch.int32)
+    out, valid = m.crop_resize_rois(frames.to(cuda_dev), boxes.to(cuda_dev), bidx.to(cuda_dev), pad=6)
+    out, valid = out.cpu(), valid.cpu().tolist()
+    for i in range(6):
+        crop = oboxes.safe_crop_ref(frames[0].numpy(), *[int(v) for v in boxes[i]], pad=6)
+        if crop is None:
+            assert valid[i] == 0 and float(out[i].abs().max()) == 0.0
+        else:
+            assert valid[i] == 1
+            assert torch.equal(out[i], oroi.classify_preprocess_ref(crop)), i
+
+
+def test_select_rois_order_and_count(cuda_dev):
+    B, max_det, nc = 5, 300, 64
+    g = torch.Generator().manual_seed(0)
+    rows = torch.zeros((B, max_det, 6))
+    rows[..., :4] = torch.rand((B, max_det, 4), generator=g) * 500
+    rows[..., 5] = torch.randint(0, nc, (B, max_det), generator=g).float()
+    count = torch.tensor([300, 0, 17, 64, 33], dtype=torch.int32)
+    det = m.Detections(rows.to(cuda_dev), torch.zeros((B, max_det), dtype=torch.int32, device=cuda_dev),
+                       count.to(cuda_dev))
+    classes = m.pipeline.RANK_CLASS_IDS
+    rb, rbatch, rdet, rcount = m.select_rois(det, classes, nc, roi_cap=B * max_det)
+    exp = [(b, i) for b in range(B) for i in range(int(count[b])) if int(rows[b, i, 5]) in classes]
+    n = int(rcount.cpu())
+    assert n == len(exp)
+    assert list(zip(rbatch[:n].cpu().tolist(), rdet[:n].cpu().tolist())) == exp
+    assert torch.equal(rb[:n].cpu(), torch.stack([rows[b, i, :4] for b, i in exp]))
+    # capacity clamp
+    _, _, _, rc2 = m.select_rois(det, classes, nc, roi_cap=5)
+    assert int(rc2.cpu()) == 5
