@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from manual_yolo_b200 import geometry, synth
-    sample = 16                                  # frames per step: bounded sample of the 64-frame batch
+    sample = BATCH                               # frames per step: the full 64-frame batch (~0.25-0.5 s of CPU work)
     in_hw = (IMGSZ, IMGSZ)
     level_hw = geometry.level_shapes(*in_hw)
     frames = synth.synth_frames(sample, *SRC_HW, seed=0).numpy()
@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(args.gpus, {"sample_frames_per_step": sample}),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} of the 64 frames of a step, {args.steps} steps, oracle port "
+                             "sample": f"{sample} frames per step (the full batch), {args.steps} steps, oracle port "
                                        "(cv2/torch-CPU/torchvision.nms/PIL leaves), all host threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -265,10 +265,10 @@ def run_ours(args, rank, world, local):
     # ---- CPU baseline (oracle port) on a bounded sample of the same workload ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        n = 16
-        fps, cores, dt = cpu_path_frames_per_s(frames_h[:n].numpy(), head_h[:n].clone(), pipe.level_hw, pipe.in_hw, 2)
+        n, passes = BATCH, 24
+        fps, cores, dt = cpu_path_frames_per_s(frames_h[:n].numpy(), head_h[:n].clone(), pipe.level_hw, pipe.in_hw, passes)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n} frames of the rank-0 batch, 1 warm-up + 2 timed passes ({dt:.1f} s), oracle port "
+               "sample": f"the rank-0 batch of {n} frames, 1 warm-up + {passes} timed passes ({dt:.1f} s), oracle port "
                          "(cv2 / torch CPU / torchvision.ops.nms / PIL), torch+cv2 threads = all cores"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,

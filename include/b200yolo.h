@@ -54,7 +54,7 @@ const char* b200yolo_strerror(int code);
  * src: B frames of H x W x 3 uint8 (BGR, interleaved), row pitch / frame stride in bytes.
  * The resized image is new_w x new_h placed at (left, top) inside outW x outH; the host computes
  * that geometry (manual_yolo_b200/geometry.py, same arithmetic as LetterBox).  Arithmetic is
- * cv2's 8-bit fixed point (11-bit coefficients), bit-exact for down-scales.
+ * cv2's 8-bit fixed point (11-bit coefficients), bit-exact for down- and up-scales.
  *   _u8_to_f32: dst = (B,3,outH,outW) float32, planes R,G,B when swap_rb != 0; value/255 (true division)
  *   _u8       : dst = (B,outH,outW,3) uint8, channel order preserved (plain LetterBox drop-in) */
 int b200yolo_letterbox_u8_to_f32(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
@@ -106,10 +106,14 @@ int b200yolo_sort_topk(const float* cand, const int* cand_anchor, const int* can
  * threshold, NaN never suppresses.  out: (B, max_det, 6) rows in kept (score-descending) order;
  * out_anchor: (B, max_det) anchor indices (UL return_idxs); out_count: (B).
  * scale: optional (B, 5) float32 {gain, pad_x, pad_y, w0, h0}: when non-NULL the boxes are also
- * mapped to source pixels as ops.scale_boxes + clip_boxes does ((x - pad) / gain, clamp). */
+ * mapped to source pixels as ops.scale_boxes + clip_boxes does ((x - pad) / gain, clamp).
+ * roi_cnt: optional (B) int32: number of kept detections of image b whose class is set in the
+ * roi_nc-bit allow-list roi_class_mask (the *_rank classes) -- consumed by
+ * b200yolo_roi_from_detections. */
 int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, const int* order, int B,
                  int cap, int max_nms, double iou_thres, float max_wh, int agnostic, int max_det,
-                 const float* scale, float* out, int* out_anchor, int* out_count, void* workspace,
+                 const float* scale, float* out, int* out_anchor, int* out_count,
+                 const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* workspace,
                  size_t workspace_bytes, void* stream);
 
 /* ---- a10: ops.scale_boxes + clip_boxes on a flat (n,>=4) xyxy array (in place) --------------- */
@@ -130,6 +134,17 @@ int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t
                              int64_t batch_stride, const float* boxes, const int* batch_idx,
                              const int* roi_count, int N, int pad, int size, float* dst, int* valid,
                              void* stream);
+
+/* Pipeline form of K5: ROI g (CTA g of roi_cap) is the g-th detection, image-major and in kept order,
+ * whose class is in class_mask; it is located on the device from det (B,max_det,6), det_count (B) and
+ * the per-image counts roi_cnt (B) written by b200yolo_nms -- no selection launch, no host round trip
+ * (the reference loops over detections on the host, detect.py:580-588).  dst: (roi_cap,3,size,size);
+ * roi_batch / roi_det / valid: (roi_cap); roi_total: (1) = min(sum roi_cnt, roi_cap). */
+int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H, int W, int64_t pitch,
+                                 int64_t batch_stride, const float* det, const int* det_count,
+                                 const int* roi_cnt, int max_det, const uint32_t* class_mask, int nc,
+                                 int pad, int size, float* dst, int* roi_batch, int* roi_det, int* valid,
+                                 int* roi_total, int roi_cap, void* stream);
 
 /* Gather the detections of selected classes (the *_rank ids) into a dense ROI list, image-major,
  * detection order preserved: feeds K5 without a host round trip (detect.py:580-588 loop).

@@ -35,7 +35,11 @@ SIGNATURES = {
     "b200yolo_sort_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "b200yolo_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_float,
-                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                             c_void_p, c_size_t, c_void_p]),
+    "b200yolo_roi_from_detections": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p,
+                                             c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "b200yolo_scale_boxes": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                                      c_void_p]),
     "b200yolo_roi_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p,

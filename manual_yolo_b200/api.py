@@ -51,6 +51,8 @@ def _class_mask(classes, nc, device):
     """Allow-list -> (ceil(nc/32),) int32 device tensor of bit words (None = all classes)."""
     if classes is None:
         return None
+    if isinstance(classes, torch.Tensor):      # prebuilt mask (Pipeline caches it: graph-capture safe)
+        return classes
     words = geometry.class_mask_words(classes, nc)
     return torch.tensor([w - (1 << 32) if w >= (1 << 31) else w for w in words], dtype=torch.int32, device=device)
 
@@ -230,8 +232,10 @@ def sort_candidates(cands: Candidates, max_nms=30000, ws: Optional[Workspace] = 
 
 
 def nms_sorted(cands: Candidates, ws: Workspace, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000,
-               max_wh=7680, scale: Optional[torch.Tensor] = None) -> Detections:
-    """K4 on candidates whose order array (``ws.order``) was filled by ``sort_candidates``."""
+               max_wh=7680, scale: Optional[torch.Tensor] = None, roi_mask: Optional[torch.Tensor] = None,
+               roi_nc=0, roi_cnt: Optional[torch.Tensor] = None) -> Detections:
+    """K4 on candidates whose order array (``ws.order``) was filled by ``sort_candidates``.
+    ``roi_mask``/``roi_cnt``: optional class allow-list mask and (B,) i32 output of per-image ROI counts."""
     if not 0 <= iou_thres <= 1:
         raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
     B = cands.rows.shape[0]
@@ -240,7 +244,8 @@ def nms_sorted(cands: Candidates, ws: Workspace, iou_thres=0.45, agnostic=False,
     rc = _lib.load().b200yolo_nms(_ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), _ptr(ws.order), B,
                                   cands.cap, int(max_nms), float(iou_thres), float(max_wh), int(bool(agnostic)),
                                   int(max_det), _ptr(scale), _ptr(ws.det.rows), _ptr(ws.det.anchor),
-                                  _ptr(ws.det.count), _ptr(ws.ws), ws.ws.numel(), _stream())
+                                  _ptr(ws.det.count), _ptr(roi_mask), int(roi_nc), _ptr(roi_cnt), _ptr(ws.ws),
+                                  ws.ws.numel(), _stream())
     _lib.check(rc, "nms")
     return ws.det
 
@@ -341,6 +346,29 @@ def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=No
                                               int(size), _ptr(out), _ptr(valid), _stream())
     _lib.check(rc, "crop_resize_rois")
     return out, valid
+
+
+def rois_from_detections(frames, det: Detections, roi_cnt, roi_mask, nc, roi_cap, pad=6, size=64, out=None):
+    """Pipeline form of K5: crops + resizes every detection whose class is in ``roi_mask`` straight from
+    the NMS output (``roi_cnt`` = per-image counts written by ``nms_sorted``).  Returns
+    (rois (roi_cap,3,size,size), roi_batch, roi_det, valid, roi_total (1,))."""
+    frames, _ = _frames_4d(frames)
+    B, H, W, _ = frames.shape
+    max_det = det.rows.shape[1]
+    dev = frames.device
+    if out is None:
+        out = (torch.empty((roi_cap, 3, size, size), dtype=torch.float32, device=dev),
+               torch.empty((roi_cap,), dtype=torch.int32, device=dev),
+               torch.empty((roi_cap,), dtype=torch.int32, device=dev),
+               torch.empty((roi_cap,), dtype=torch.int32, device=dev),
+               torch.empty((1,), dtype=torch.int32, device=dev))
+    rc = _lib.load().b200yolo_roi_from_detections(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0),
+                                                  _ptr(det.rows), _ptr(det.count), _ptr(roi_cnt), max_det,
+                                                  _ptr(roi_mask), int(nc), int(pad), int(size), _ptr(out[0]),
+                                                  _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(out[4]),
+                                                  int(roi_cap), _stream())
+    _lib.check(rc, "rois_from_detections")
+    return out
 
 
 def select_rois(det: Detections, classes, nc, roi_cap, out=None):

@@ -38,6 +38,19 @@ __device__ __forceinline__ void cv_linear_tap(int d, double scale, int ssize, in
   a1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
+// Vertical axis: cv::resize keeps the fractional weights of out-of-range taps and only clamps the
+// source ROW indices in its row loop (matters on up-scales: the first/last rows blend one source
+// row twice, with two separately truncated products).
+__device__ __forceinline__ void cv_linear_tap_v(int d, double scale, int ssize, int& r0, int& r1, int& b0, int& b1) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  const int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  b0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  b1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  r0 = min(max(s, 0), ssize - 1);
+  r1 = min(max(s + 1, 0), ssize - 1);
+}
+
 // 6 consecutive bytes (two BGR pixels) starting at byte offset `off` of a staged row.
 __device__ __forceinline__ void load6(const uint8_t* row, int off, uint32_t& lo, uint32_t& hi) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + (off >> 2);
@@ -91,27 +104,28 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LbParams p) {
   const OutT padv = lb_cast<OutT>(p.pad_value);
 
   const bool interior = (oy >= p.top) && (oy < p.top + p.new_h);
-  int sy = 0, b0 = 2048, b1 = 0;
-  if (interior) cv_linear_tap(oy - p.top, p.scale_y, p.H, sy, b0, b1);
+  int sy = 0, sy1 = 0, b0 = 2048, b1 = 0;
+  if (interior) cv_linear_tap_v(oy - p.top, p.scale_y, p.H, sy, sy1, b0, b1);
   const bool two_rows = interior && (b1 != 0);
+  const bool load_row1 = two_rows && (sy1 != sy);
   uint8_t* row0 = smem;
-  uint8_t* row1 = smem + p.row_smem;
+  uint8_t* row1 = load_row1 ? smem + p.row_smem : smem;   // clamped rows alias the same staged row
 
   if (interior) {
     const uint8_t* g0 = p.src + (int64_t)b * p.bstride + (int64_t)sy * p.pitch;
-    const uint8_t* g1 = p.src + (int64_t)b * p.bstride + (int64_t)min(sy + 1, p.H - 1) * p.pitch;
+    const uint8_t* g1 = p.src + (int64_t)b * p.bstride + (int64_t)sy1 * p.pitch;
     if (p.bulk_ok) {
       if (tid == 0) {
         b200::mbar_init(&bar, 1);
         b200::mbar_fence_init();
-        b200::mbar_expect_tx(&bar, two_rows ? 2u * p.row_bytes : (uint32_t)p.row_bytes);
+        b200::mbar_expect_tx(&bar, load_row1 ? 2u * p.row_bytes : (uint32_t)p.row_bytes);
         b200::bulk_g2s(row0, g0, p.row_bytes, &bar);
-        if (two_rows) b200::bulk_g2s(row1, g1, p.row_bytes, &bar);
+        if (load_row1) b200::bulk_g2s(row1, g1, p.row_bytes, &bar);
       }
     } else {
       for (int i = tid; i < p.row_bytes; i += blockDim.x) {
         row0[i] = g0[i];
-        if (two_rows) row1[i] = g1[i];
+        if (load_row1) row1[i] = g1[i];
       }
     }
   }

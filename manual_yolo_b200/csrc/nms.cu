@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
                                                  int cap, int max_nms, double thr, float max_wh, int agnostic,
                                                  int max_det, const float* __restrict__ scale,
                                                  float* __restrict__ out, int* __restrict__ out_anchor,
-                                                 int* __restrict__ out_count, float4* __restrict__ ws, int smem_boxes) {
+                                                 int* __restrict__ out_count, const uint32_t* __restrict__ roi_mask,
+                                                 int roi_nc, int* __restrict__ roi_cnt, float4* __restrict__ ws,
+                                                 int smem_boxes) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float4* sbox = reinterpret_cast<float4*>(smem_raw);
   uint8_t* removed = reinterpret_cast<uint8_t*>(sbox + smem_boxes);   // [smem_boxes or n]
@@ -51,13 +53,14 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
   __shared__ unsigned rem_bits[2];
   __shared__ unsigned long long kept_bits_s;
   __shared__ int kcount_s;
+  __shared__ int roi_s;
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = min(min(min(cand_count[b], cap), max_nms), B200YOLO_MAX_SORT);
   const float* crow = cand + (int64_t)b * cap * 6;
   const int* orow = order + (int64_t)b * cap;
   if (n <= 0) {
-    if (tid == 0) out_count[b] = 0;
+    if (tid == 0) { out_count[b] = 0; if (roi_cnt) roi_cnt[b] = 0; }
     return;
   }
   float4* box = sbox;
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
     box[r] = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
     rem[r] = 0;
   }
-  if (tid == 0) kcount_s = 0;
+  if (tid == 0) { kcount_s = 0; roi_s = 0; }
   __syncthreads();
 
   for (int s = 0; s < n; s += kChunk) {
@@ -160,8 +163,13 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
     float* o = out + ((int64_t)b * max_det + r) * 6;
     o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = row[4]; o[5] = row[5];
     out_anchor[(int64_t)b * max_det + r] = cand_anchor[(int64_t)b * cap + slot];
+    if (roi_cnt) {  // kept detections whose class feeds the ROI stage (the *_rank ids)
+      const int c = (int)row[5];
+      if (c >= 0 && c < roi_nc && ((roi_mask[c >> 5] >> (c & 31)) & 1u)) atomicAdd(&roi_s, 1);
+    }
   }
-  if (tid == 0) out_count[b] = kc;
+  __syncthreads();
+  if (tid == 0) { out_count[b] = kc; if (roi_cnt) roi_cnt[b] = roi_s; }
 }
 
 __global__ void scale_boxes_kernel(float* boxes, int n, int row_stride, float gain, float padx, float pady,
@@ -179,12 +187,14 @@ __global__ void scale_boxes_kernel(float* boxes, int n, int row_stride, float ga
 
 extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, const int* order,
                             int B, int cap, int max_nms, double iou_thres, float max_wh, int agnostic, int max_det,
-                            const float* scale, float* out, int* out_anchor, int* out_count, void* workspace,
+                            const float* scale, float* out, int* out_anchor, int* out_count,
+                            const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* workspace,
                             size_t workspace_bytes, void* stream) {
   B200_REQUIRE(cand && cand_anchor && cand_count && order && out && out_anchor && out_count, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && cap > 0 && max_nms > 0 && max_det > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(cap <= B200YOLO_MAX_SORT && max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
   B200_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, B200YOLO_ERR_RANGE);
+  B200_REQUIRE(roi_cnt == nullptr || (roi_class_mask != nullptr && roi_nc > 0), B200YOLO_ERR_NULL);
   if (cap > kSmemBoxesMax) {
     B200_REQUIRE(workspace, B200YOLO_ERR_NULL);
     B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
@@ -201,14 +211,16 @@ extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int
       if (e != cudaSuccess) return (int)e;
     }
     kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                             max_det, scale, out, out_anchor, out_count, (float4*)workspace, smem_boxes);
+                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt,
+                             (float4*)workspace, smem_boxes);
   } else {
     constexpr int NT = 1024;
     auto kern = nms_kernel<NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                             max_det, scale, out, out_anchor, out_count, (float4*)workspace, smem_boxes);
+                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt,
+                             (float4*)workspace, smem_boxes);
   }
   return b200_launch_status();
 }

@@ -73,24 +73,31 @@ __device__ __forceinline__ int half_round_even(int d) {
   return (d & 1) ? ((k & 1) ? k + 1 : k) : k;
 }
 
-__global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict__ frames, int B, int H, int W,
-                                                       int64_t pitch, int64_t bstride,
-                                                       const float* __restrict__ boxes,
-                                                       const int* __restrict__ batch_idx,
-                                                       const int* __restrict__ roi_count, int pad, int S,
-                                                       float* __restrict__ dst, int* __restrict__ valid) {
-  extern __shared__ __align__(16) uint8_t roi_smem[];
-  AxisPlan& px = *reinterpret_cast<AxisPlan*>(roi_smem);
-  AxisPlan& py = *reinterpret_cast<AxisPlan*>(roi_smem + sizeof(AxisPlan));
-  uint8_t (*strip)[kMaxSize][3] = reinterpret_cast<uint8_t (*)[kMaxSize][3]>(roi_smem + 2 * sizeof(AxisPlan));
-  const int r = blockIdx.x, tid = threadIdx.x;
-  if (roi_count != nullptr && r >= *roi_count) return;
-  float* out = dst + (int64_t)r * 3 * S * S;
+// Word load that never touches bytes outside [lo, hi) (the caller's frame buffer).
+__device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* a, const uint8_t* lo, const uint8_t* hi) {
+  if (a >= lo && a + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(a));
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (a + k >= lo && a + k < hi) w |= (uint32_t)__ldg(a + k) << (8 * k);
+  return w;
+}
 
-  // ---- integer crop geometry: int() truncation then safe_crop (detect.py:100-113) ----
-  const int bi = batch_idx[r];
-  const int bx1 = __float2int_rz(boxes[r * 4 + 0]), by1 = __float2int_rz(boxes[r * 4 + 1]);
-  const int bx2 = __float2int_rz(boxes[r * 4 + 2]), by2 = __float2int_rz(boxes[r * 4 + 3]);
+struct RoiSmem {
+  AxisPlan px, py;
+  uint8_t strip[kRowsMax][kMaxSize][3];
+  int sel[4];
+};
+constexpr int kStageBytes = 64 * 1024;   // staged crop rows (typical rank crop: ~36 KB)
+
+// One ROI per CTA.  (bi, x1..y2) already int()-truncated box in source pixels.
+__device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_lo, const uint8_t* buf_hi, int B, int H,
+                         int W, int64_t pitch, int64_t bstride, int bi, int bx1, int by1, int bx2, int by2, int pad, int S,
+                         float* __restrict__ out, int* __restrict__ valid_out, RoiSmem& sm, uint8_t* stage) {
+  const int tid = threadIdx.x;
+  AxisPlan& px = sm.px;
+  AxisPlan& py = sm.py;
+  // ---- safe_crop (detect.py:100-113) ----
   const int cx1 = max(0, min(W - 1, bx1 - pad)), cx2 = max(0, min(W, bx2 + pad));
   const int cy1 = max(0, min(H - 1, by1 - pad)), cy2 = max(0, min(H, by2 + pad));
   const int cw = cx2 - cx1, ch = cy2 - cy1;
@@ -102,12 +109,12 @@ __global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict
     else new_w = __double2int_rz(__ddiv_rn((double)(S * (int64_t)cw), (double)ch));
     // supported envelope of the shared-memory plan: ksize = ceil(support)*2+1 <= kMaxTaps on both axes
     const double sx = (double)cw / (double)new_w, sy = (double)ch / (double)new_h;
-    const double sm = fmax(fmax(sx, sy), 1.0);
-    if (2 * (int)ceil(sm) + 1 > kMaxTaps) { ok = false; unsupported = true; }
+    const double smx = fmax(fmax(sx, sy), 1.0);
+    if (2 * (int)ceil(smx) + 1 > kMaxTaps) { ok = false; unsupported = true; }
   }
   if (!ok) {
     for (int i = tid; i < 3 * S * S; i += kThreads) out[i] = 0.f;
-    if (tid == 0) valid[r] = unsupported ? -1 : 0;
+    if (tid == 0) *valid_out = unsupported ? -1 : 0;
     return;
   }
   const int left = half_round_even(new_w - S), top = half_round_even(new_h - S);
@@ -117,22 +124,51 @@ __global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict
   __syncthreads();
 
   const uint8_t* crop = frames + (int64_t)bi * bstride + (int64_t)cy1 * pitch + (int64_t)cx1 * 3;
+  // horizontal span of source columns the 64 surviving output columns reference
+  const int x_lo = px.bounds[0][0];
+  const int x_hi = px.bounds[S - 1][0] + px.bounds[S - 1][1];
+  const int span_bytes = (x_hi - x_lo) * 3;
+  const int row_words = (span_bytes + 3 + 3) / 4;          // any 4-byte phase fits
+  const int row_stride = row_words * 4;
   int t0 = 0;
   while (t0 < S) {
-    // vertical tile [t0, t1): input rows [rmin, rmax) must fit the strip
+    // vertical tile [t0, t1): input rows [rmin, rmax) must fit the strip (and, when staged, the stage)
     const int rmin = py.bounds[t0][0];
+    const int rows_cap = min(kRowsMax, kStageBytes / row_stride);
+    const bool staged = rows_cap >= py.bounds[t0][1];
+    const int cap_rows = staged ? rows_cap : kRowsMax;
     int t1 = t0 + 1;
-    while (t1 < S && py.bounds[t1][0] + py.bounds[t1][1] - rmin <= kRowsMax) ++t1;
+    while (t1 < S && py.bounds[t1][0] + py.bounds[t1][1] - rmin <= cap_rows) ++t1;
     const int rmax = py.bounds[t1 - 1][0] + py.bounds[t1 - 1][1];
     const int rows = rmax - rmin;
-    // ---- horizontal pass: strip[row][xx][c] = clip8(2^21 + sum px * k) ----
-    for (int e = tid; e < rows * S * 3; e += kThreads) {
-      const int c = e % 3, xx = (e / 3) % S, rr = e / (3 * S);
-      const int xmin = px.bounds[xx][0], cnt = px.bounds[xx][1];
-      const uint8_t* p = crop + (int64_t)(rmin + rr) * pitch + xmin * 3 + c;
-      int acc = 1 << (kPrec - 1);
-      for (int x = 0; x < cnt; ++x) acc += (int)__ldg(p + x * 3) * px.coef[xx][x];
-      strip[rr][xx][c] = (uint8_t)clip8(acc);
+    if (staged) {
+      // ---- stage the referenced crop rows: coalesced 4-byte loads, all in flight at once ----
+      for (int e = tid; e < rows * row_words; e += kThreads) {
+        const int rr = e / row_words, wd = e - rr * row_words;
+        const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+        const uint8_t* ga = g - (reinterpret_cast<uintptr_t>(g) & 3) + wd * 4;
+        reinterpret_cast<uint32_t*>(stage + rr * row_stride)[wd] = load_word_guarded(ga, buf_lo, buf_hi);
+      }
+      __syncthreads();
+      for (int e = tid; e < rows * S * 3; e += kThreads) {
+        const int c = e % 3, xx = (e / 3) % S, rr = e / (3 * S);
+        const int xmin = px.bounds[xx][0], cnt = px.bounds[xx][1];
+        const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+        const uint8_t* p = stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + (xmin - x_lo) * 3 + c;
+        int acc = 1 << (kPrec - 1);
+        for (int x = 0; x < cnt; ++x) acc += (int)p[x * 3] * px.coef[xx][x];
+        sm.strip[rr][xx][c] = (uint8_t)clip8(acc);
+      }
+    } else {
+      // ---- oversize ROI: horizontal pass straight from global memory ----
+      for (int e = tid; e < rows * S * 3; e += kThreads) {
+        const int c = e % 3, xx = (e / 3) % S, rr = e / (3 * S);
+        const int xmin = px.bounds[xx][0], cnt = px.bounds[xx][1];
+        const uint8_t* p = crop + (int64_t)(rmin + rr) * pitch + xmin * 3 + c;
+        int acc = 1 << (kPrec - 1);
+        for (int x = 0; x < cnt; ++x) acc += (int)__ldg(p + x * 3) * px.coef[xx][x];
+        sm.strip[rr][xx][c] = (uint8_t)clip8(acc);
+      }
     }
     __syncthreads();
     // ---- vertical pass + BGR->RGB + /255 ----
@@ -141,13 +177,101 @@ __global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict
       const int xx = e % S, yy = t0 + (e / S) % trows, c = e / (S * trows);
       const int ymin = py.bounds[yy][0], cnt = py.bounds[yy][1];
       int acc = 1 << (kPrec - 1);
-      for (int y = 0; y < cnt; ++y) acc += (int)strip[ymin - rmin + y][xx][c] * py.coef[yy][y];
+      for (int y = 0; y < cnt; ++y) acc += (int)sm.strip[ymin - rmin + y][xx][c] * py.coef[yy][y];
       out[((2 - c) * S + yy) * S + xx] = b200::u8_div255(clip8(acc));
     }
     __syncthreads();
     t0 = t1;
   }
-  if (tid == 0) valid[r] = 1;
+  if (tid == 0) *valid_out = 1;
+}
+
+// ROI list form: boxes (N,4) float + batch_idx (N).
+__global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B,
+                                                       int H, int W, int64_t pitch, int64_t bstride,
+                                                       const float* __restrict__ boxes,
+                                                       const int* __restrict__ batch_idx,
+                                                       const int* __restrict__ roi_count, int pad, int S,
+                                                       float* __restrict__ dst, int* __restrict__ valid) {
+  extern __shared__ __align__(16) uint8_t roi_smem[];
+  RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
+  uint8_t* stage = roi_smem + ((sizeof(RoiSmem) + 15) & ~(size_t)15);
+  const int r = blockIdx.x;
+  if (roi_count != nullptr && r >= *roi_count) return;
+  // int() truncation of the float box (detect.py:581)
+  roi_body(frames, frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
+           __float2int_rz(boxes[r * 4 + 1]), __float2int_rz(boxes[r * 4 + 2]), __float2int_rz(boxes[r * 4 + 3]), pad, S,
+           dst + (int64_t)r * 3 * S * S, valid + r, sm, stage);
+}
+
+// Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
+// the allow-list, from the per-image counts the NMS kernel wrote -- no separate selection launch.
+__global__ void __launch_bounds__(kThreads) roi_det_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi,
+                                                           int B, int H, int W, int64_t pitch, int64_t bstride,
+                                                           const float* __restrict__ det,
+                                                           const int* __restrict__ det_count,
+                                                           const int* __restrict__ roi_cnt, int max_det,
+                                                           const uint32_t* __restrict__ class_mask, int nc, int pad,
+                                                           int S, float* __restrict__ dst, int* __restrict__ roi_batch,
+                                                           int* __restrict__ roi_det, int* __restrict__ valid,
+                                                           int* __restrict__ roi_total, int roi_cap) {
+  extern __shared__ __align__(16) uint8_t roi_smem[];
+  RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
+  uint8_t* stage = roi_smem + ((sizeof(RoiSmem) + 15) & ~(size_t)15);
+  __shared__ int wsum[kThreads / 32];
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // ---- (1) which image: running prefix over roi_cnt[0..B) in chunks of kThreads ----
+  if (tid == 0) { sm.sel[0] = -1; sm.sel[1] = 0; sm.sel[2] = 0; }
+  int carry = 0;
+  for (int base = 0; base < B; base += kThreads) {
+    const int b = base + tid;
+    const int v = b < B ? roi_cnt[b] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { if (w < wid) wbase += wsum[w]; tot += wsum[w]; }
+    const int excl = carry + wbase + inc - v;
+    if (b < B && g >= excl && g < excl + v) { sm.sel[0] = b; sm.sel[1] = g - excl; }
+    carry += tot;
+    __syncthreads();
+  }
+  if (g == 0 && tid == 0) *roi_total = min(carry, roi_cap);
+  __syncthreads();
+  const int b = sm.sel[0], k = sm.sel[1];
+  if (b < 0) return;                       // g >= number of ROIs in this batch
+  // ---- (2) the k-th allowed detection of image b, in kept (score) order ----
+  const int n = min(det_count[b], max_det);
+  int seen = 0;
+  for (int base = 0; base < n; base += kThreads) {
+    const int i = base + tid;
+    bool w = false;
+    if (i < n) {
+      const int c = (int)det[((int64_t)b * max_det + i) * 6 + 5];
+      w = c >= 0 && c < nc && ((class_mask[c >> 5] >> (c & 31)) & 1u);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, w);
+    if (lane == 0) wsum[wid] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < kThreads / 32; ++ww) { if (ww < wid) wbase += wsum[ww]; tot += wsum[ww]; }
+    if (w && seen + wbase + __popc(bal & ((1u << lane) - 1u)) == k) sm.sel[2] = i;
+    seen += tot;
+    __syncthreads();
+    if (seen > k) break;
+  }
+  const int i = sm.sel[2];
+  const float* row = det + ((int64_t)b * max_det + i) * 6;
+  if (tid == 0) { roi_batch[g] = b; roi_det[g] = i; }
+  roi_body(frames, frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
+           __float2int_rz(row[2]), __float2int_rz(row[3]), pad, S, dst + (int64_t)g * 3 * S * S, valid + g, sm, stage);
 }
 
 // ---- ROI selection: detections of the allowed classes -> dense list, image-major, order kept ----
@@ -229,6 +353,8 @@ __global__ void __launch_bounds__(1024) select_rois_kernel(const float* __restri
 
 }  // namespace
 
+static size_t roi_smem_bytes() { return ((sizeof(RoiSmem) + 15) & ~(size_t)15) + kStageBytes; }
+
 extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t pitch,
                                         int64_t batch_stride, const float* boxes, const int* batch_idx,
                                         const int* roi_count, int N, int pad, int size, float* dst, int* valid,
@@ -238,11 +364,33 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
   B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
   B200_REQUIRE(size > 0 && size <= kMaxSize, B200YOLO_ERR_UNSUPPORTED);
   if (N == 0) return B200YOLO_OK;
-  const size_t smem = 2 * sizeof(AxisPlan) + (size_t)kRowsMax * kMaxSize * 3;
+  const size_t smem = roi_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, B, H, W, pitch, batch_stride, boxes, batch_idx,
-                                                       roi_count, pad, size, dst, valid);
+  const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
+  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
+                                                           batch_idx, roi_count, pad, size, dst, valid);
+  return b200_launch_status();
+}
+
+extern "C" int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H, int W, int64_t pitch,
+                                            int64_t batch_stride, const float* det, const int* det_count,
+                                            const int* roi_cnt, int max_det, const uint32_t* class_mask, int nc,
+                                            int pad, int size, float* dst, int* roi_batch, int* roi_det, int* valid,
+                                            int* roi_total, int roi_cap, void* stream) {
+  B200_REQUIRE(frames && det && det_count && roi_cnt && class_mask && dst && roi_batch && roi_det && valid && roi_total,
+               B200YOLO_ERR_NULL);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && max_det > 0 && nc > 0 && roi_cap > 0 && pad >= 0, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(size > 0 && size <= kMaxSize, B200YOLO_ERR_UNSUPPORTED);
+  const size_t smem = roi_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(roi_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
+  roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, det,
+                                                                    det_count, roi_cnt, max_det, class_mask, nc, pad,
+                                                                    size, dst, roi_batch, roi_det, valid, roi_total,
+                                                                    roi_cap);
   return b200_launch_status();
 }
 

@@ -6,8 +6,8 @@ This is the batched, device-resident form of the reference's per-frame loop
 preprocessing (``detect.py:121``).  The backbone/neck stay torch modules outside this package: the
 Detect-head tensor is an input here (``head``), the letterboxed network input an output (``net_in``).
 
-All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 7 launches of
-this package's kernels plus two counter memsets, capturable into one CUDA graph.
+All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 5 launches of
+this package's kernels plus one counter memset, capturable into one CUDA graph.
 """
 
 from __future__ import annotations
@@ -20,7 +20,7 @@ import torch
 from . import api, geometry
 
 RANK_CLASS_IDS = (6, 11, 16, 21, 26, 37, 43)  # *_rank classes, roadmap1.v3i.yolov8/data.yaml:6
-GPU_LAUNCHES_PER_STEP = 6                      # letterbox, decode_filter, sort, nms, select_rois, roi
+GPU_LAUNCHES_PER_STEP = 5                      # letterbox, decode_filter, sort_topk, nms, roi_from_detections
 
 
 @dataclass
@@ -63,12 +63,14 @@ class Pipeline:
         self.ws = api.Workspace(B, self.cap, max_det, dev)
         self.scale = api.scale_params_tensor(self.in_hw, [self.src_hw] * B, dev)
         self.roi_cap = max(1, B * int(rois_per_frame))
-        self.roi_buf = (torch.empty((self.roi_cap, 4), dtype=torch.float32, device=dev),
-                        torch.empty((self.roi_cap,), dtype=torch.int32, device=dev),
-                        torch.empty((self.roi_cap,), dtype=torch.int32, device=dev),
+        self.cls_mask = api._class_mask(classes, self.nc, dev)
+        self.roi_mask = api._class_mask(self.roi_classes, self.nc, dev)
+        self.roi_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.roi_out = (torch.zeros((self.roi_cap, 3, roi_size, roi_size), dtype=torch.float32, device=dev),
+                        torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
                         torch.zeros((1,), dtype=torch.int32, device=dev))
-        self.rois = torch.zeros((self.roi_cap, 3, roi_size, roi_size), dtype=torch.float32, device=dev)
-        self.roi_valid = torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev)
         self._graph = None
         self._static = None
         self._prof = None
@@ -84,21 +86,18 @@ class Pipeline:
         api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
                        out=self.net_in)
         t("decode_filter")
-        api.decode_and_filter(head, self.strides, self.conf, self.classes, level_hw=self.level_hw,
+        api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
                               cap=self.cap, out=self.cands)
         t("sort_topk")
         api.sort_candidates(self.cands, self.max_nms, self.ws)
         t("nms")
         det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
-                             scale=self.scale)
-        t("select_rois")
-        api.select_rois(det, self.roi_classes, self.nc, self.roi_cap, out=self.roi_buf)
+                             scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
         t("roi_crop_resize")
-        api.crop_resize_rois(frames, self.roi_buf[0], self.roi_buf[1], self.pad, self.roi_size,
-                             roi_count=self.roi_buf[3], out=self.rois, valid=self.roi_valid)
+        ro = api.rois_from_detections(frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
+                                      self.roi_size, out=self.roi_out)
         t(None)
-        return PipelineResult(self.net_in, det, self.cands.count, self.rois, self.roi_buf[1], self.roi_buf[2],
-                              self.roi_valid, self.roi_buf[3])
+        return PipelineResult(self.net_in, det, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
 
     # -- per-kernel CUDA-event timing (bench.py): events on the launching stream around each stage --
     def enable_profiling(self, on=True):

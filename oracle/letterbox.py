@@ -66,33 +66,39 @@ def preprocess_ref(frames, new_shape=(640, 640), auto=False, stride=32):
 # It is the *specification* the CUDA kernel follows; tests check it bit-for-bit against cv2.
 # --------------------------------------------------------------------------------------------
 
-def cv2_linear_axis_table(ssize: int, dsize: int):
-    """Per-axis (index, a0, a1) of cv2's 8-bit INTER_LINEAR: 11-bit coefficients."""
+def cv2_linear_axis_table(ssize: int, dsize: int, vertical: bool = False):
+    """Per-axis (index0, index1, a0, a1) of cv2's 8-bit INTER_LINEAR: 11-bit coefficients.
+
+    Horizontal axis: taps outside the image are CLAMPED WITH THE FRACTION RESET (``fx = 0``).
+    Vertical axis: cv::resize keeps the fractional weights and only clamps the source ROW indices
+    (``clip(sy + k, 0, ssize)`` in the row loop), so on up-scales the first/last rows blend the same
+    source row twice with two separately truncated products.  Identical for every down-scale."""
     scale = 1.0 / (dsize / ssize)  # double, exactly as cv::resize: inv_scale = dsize/ssize; scale = 1/inv
     d = np.arange(dsize, dtype=np.float64)
     f = ((d + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int32)
     f = (f - s.astype(np.float32)).astype(np.float32)
-    lo = s < 0
-    f[lo] = 0.0
-    s[lo] = 0
-    hi = s >= ssize - 1
-    f[hi] = 0.0
-    s[hi] = ssize - 1
+    if not vertical:
+        lo = s < 0
+        f[lo] = 0.0
+        s[lo] = 0
+        hi = s >= ssize - 1
+        f[hi] = 0.0
+        s[hi] = ssize - 1
     a0 = np.rint((np.float32(1.0) - f) * np.float32(2048.0)).astype(np.int32)
     a1 = np.rint(f * np.float32(2048.0)).astype(np.int32)
-    return s, a0, a1
+    s0 = np.clip(s, 0, ssize - 1)
+    s1 = np.clip(s + 1, 0, ssize - 1)
+    return s0, s1, a0, a1
 
 
 def cv2_resize_linear_restated(img, dsize_wh):
-    """Bit-exact (for down-scales) restatement of cv2.resize(img, dsize, INTER_LINEAR), u8 HWC."""
+    """Bit-exact restatement of cv2.resize(img, dsize, INTER_LINEAR) on u8 HWC (down- and up-scales)."""
     H, W = img.shape[:2]
     dw, dh = int(dsize_wh[0]), int(dsize_wh[1])
-    sx, ax0, ax1 = cv2_linear_axis_table(W, dw)
-    sy, ay0, ay1 = cv2_linear_axis_table(H, dh)
+    sx, sx1, ax0, ax1 = cv2_linear_axis_table(W, dw)
+    sy, sy1, ay0, ay1 = cv2_linear_axis_table(H, dh, vertical=True)
     src = img.astype(np.int32)
-    sx1 = np.minimum(sx + 1, W - 1)
-    sy1 = np.minimum(sy + 1, H - 1)
     # horizontal pass on the two referenced rows
     r0 = src[sy]            # (dh, W, C)
     r1 = src[sy1]

@@ -19,7 +19,7 @@ def _declared_symbols():
 def test_header_symbols_exported_and_bound():
     lib = _lib.load()
     names = _declared_symbols()
-    assert len(names) >= 12
+    assert len(names) >= 13
     for n in names:
         assert hasattr(lib, n), f"{n} declared in b200yolo.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
@@ -44,7 +44,8 @@ def test_argument_errors_before_any_launch():
     assert lib.b200yolo_letterbox_u8_to_f32(one, 1, 8, 8, 24, 192, one, 8, 8, 8, 8, 0, 0, 300, 1, null) == -6
     assert lib.b200yolo_filter_decoded(one, 1, 10, 6, 100, 1.5, null, one, one, one, 100, null) == -6
     assert lib.b200yolo_filter_decoded(one, 1, 8, 6, 100, 0.5, null, one, one, one, 100, null) == -2
-    assert lib.b200yolo_nms(one, one, one, one, 1, 100, 30000, 2.0, 7680.0, 0, 300, null, one, one, one, null, 0, null) == -6
+    assert lib.b200yolo_nms(one, one, one, one, 1, 100, 30000, 2.0, 7680.0, 0, 300, null, one, one, one, null, 0, null, null, 0, null) == -6
+    assert lib.b200yolo_nms(one, one, one, one, 1, 100, 30000, 0.5, 7680.0, 0, 300, null, one, one, one, null, 0, one, null, 0, null) == -1
     assert lib.b200yolo_sort_topk(one, one, one, 1, 70000, 30000, one, null, 0, null) == -4
     assert lib.b200yolo_sort_topk(one, one, one, 1, 20000, 30000, one, null, 0, null) == -1   # needs workspace
     assert lib.b200yolo_roi_crop_resize(one, 1, 8, 8, 24, 192, one, one, null, 4, 6, 128, one, one, null) == -4

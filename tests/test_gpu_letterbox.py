@@ -69,13 +69,14 @@ def test_pitched_and_single_image_inputs(cuda_dev):
                           olb.letterbox_ref(h, (128, 256), padding_value=0))
 
 
-@pytest.mark.parametrize("hw,new", [((543, 770), 1280), ((300, 400), 640)])
-def test_upscale_within_one_lsb(cuda_dev, hw, new):
-    """Up-scaling (only pipe.py's imgsz=1280 case) is outside the BASELINE configs; cv2's own arithmetic
-    is not fully restated there: tolerance 1 LSB, mismatch fraction reported."""
-    f = _frames(hw, 3)
-    got = m.letterbox(torch.from_numpy(f).to(cuda_dev), (new, new), auto=True).cpu().numpy().astype(np.int32)
-    ref = np.stack([olb.letterbox_ref(x, (new, new), auto=True) for x in f]).astype(np.int32)
-    d = np.abs(got - ref)
-    assert d.max() <= 1
-    assert (d != 0).mean() < 0.01
+@pytest.mark.parametrize("hw,new", [((543, 770), 1280), ((300, 400), 640), ((37, 53), 640), ((100, 200), (128, 256))])
+def test_upscale_bit_exact(cuda_dev, hw, new):
+    """Up-scaling (pipe.py's imgsz=1280 on a 770x543 capture): the vertical axis keeps the fractional
+    weights of clamped taps (cv::resize clamps row indices only) -- restated, so also bit-exact."""
+    f = _frames(hw, 3, B=2)
+    new = (new, new) if isinstance(new, int) else new
+    got = m.letterbox(torch.from_numpy(f).to(cuda_dev), new, auto=True).cpu().numpy()
+    ref = np.stack([olb.letterbox_ref(x, new, auto=True) for x in f])
+    assert np.array_equal(got, ref)
+    assert torch.equal(m.preprocess(torch.from_numpy(f).to(cuda_dev), new, auto=True).cpu(),
+                       olb.preprocess_ref(list(f), new, auto=True))

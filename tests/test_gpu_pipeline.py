@@ -22,20 +22,21 @@ def _oracle_chain(frames, head, pipe, conf, iou):
     net_in = olb.preprocess_ref(list(frames), pipe.new_shape, auto=pipe.auto)
     pred = ohead.detect_inference_ref(head, pipe.level_hw)
     out, idx = onms.non_max_suppression_ref(pred, conf, iou, return_idxs=True)
-    dets, rois = [], []
+    dets, rois, where = [], [], []
     for b, o in enumerate(out):
         o = o.clone()
         o[:, :4] = oboxes.scale_boxes_ref(pipe.in_hw, o[:, :4], (H, W))
         dets.append(o)
-        for row in o:
+        for i, row in enumerate(o):
             if int(row[5]) in m.pipeline.RANK_CLASS_IDS:
                 crop = oboxes.safe_crop_ref(frames[b], *[int(v) for v in row[:4]], pad=6)
                 rois.append(None if crop is None else oroi.classify_preprocess_ref(crop))
-    return net_in, dets, idx, rois
+                where.append((b, i))
+    return net_in, dets, idx, rois, where
 
 
 def _assert_matches(res, ref, B):
-    net_in, dets, idx, rois = ref
+    net_in, dets, idx, rois, where = ref
     assert torch.equal(res.net_in.cpu(), net_in)
     counts = res.det.count.cpu().tolist()
     for b in range(B):
@@ -47,6 +48,7 @@ def _assert_matches(res, ref, B):
             assert (got[:, :5] - dets[b][:, :5]).abs().max().item() <= 1e-4
     n = int(res.roi_count.cpu())
     assert n == len(rois)
+    assert list(zip(res.roi_batch[:n].cpu().tolist(), res.roi_det[:n].cpu().tolist())) == where
     for i, r in enumerate(rois):
         if r is None:
             assert int(res.roi_valid[i]) == 0

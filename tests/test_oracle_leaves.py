@@ -29,7 +29,8 @@ def test_letterbox_geometry(hw, new, auto, exp):
 
 @pytest.mark.parametrize("src,dst", [((900, 1600), (640, 360)), ((1200, 1920), (640, 400)),
                                      ((1130, 930), (527, 640)), ((543, 770), (640, 451)),
-                                     ((1194, 1919), (640, 398)), ((1034, 1700), (640, 389))])
+                                     ((1194, 1919), (640, 398)), ((1034, 1700), (640, 389)),
+                                     ((543, 770), (1280, 903)), ((100, 200), (256, 128)), ((5, 7), (640, 457))])
 def test_cv2_resize_restated_bit_exact(src, dst):
     rng = np.random.default_rng(src[0] + dst[0])
     img = rng.integers(0, 256, (src[0], src[1], 3), dtype=np.uint8)
