@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""bench_extra.py -- the BASELINE.json configs that are not the headline line (parity cases with timings):
+
+  config 3  NMS-heavy eval regime: (256,144,8400) head, nc=80, conf=0.001, max_det=300, iou 0.7 / 0.45
+            -> decode us, sort us, NMS us per batch and per image
+  config 4  ROI chain: 4096 rank-box crops -> (4096,3,64,64) fp32
+  config 1  B=1 test2.png-shaped frame (1600x900), both letterbox modes, nc=64, conf 0.25
+
+Prints one JSON object (also written to --out).  CUDA events on the launching stream, 3 warm-ups,
+inputs re-used (these are latency numbers; the L2 state is stated per entry).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import manual_yolo_b200 as m  # noqa: E402
+from manual_yolo_b200 import geometry, synth  # noqa: E402
+
+
+def timed(fn, iters=10, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return {"us_median": statistics.median(ts), "us_min": min(ts), "iters": iters}
+
+
+def config3(dev, B=256, nc=80, cpu_images=4):
+    lv = geometry.level_shapes(640, 640)
+    parts = [synth.synth_head_dense(64, nc, seed=s) for s in range(B // 64)]
+    head = torch.cat(parts).to(dev)
+    out = {"shape": list(head.shape), "conf": 0.001, "max_det": 300,
+           "l2": "head 1.24 GB streams from HBM; candidate arrays (57 MB) are L2-resident"}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    cands = m.decode_and_filter(head, conf_thres=0.001, level_hw=lv)
+    ws = m.Workspace(B, cands.cap, 300, dev)
+    out["candidates_per_image_mean"] = float(cands.count.float().mean())
+
+    def dec():
+        cands.count.zero_()
+        m.decode_and_filter(head, conf_thres=0.001, level_hw=lv, out=cands)
+    out["decode_filter"] = timed(dec, flush=flush)
+    out["decode_filter"]["algo_GBps"] = head.numel() * 4 / (out["decode_filter"]["us_median"] * 1e-6) / 1e9
+    out["sort_topk"] = timed(lambda: m.sort_candidates(cands, 30000, ws))
+    for iou in (0.7, 0.45):
+        r = timed(lambda: m.nms_sorted(cands, ws, iou, max_det=300))
+        r["us_per_image"] = r["us_median"] / B
+        out[f"nms_iou{iou}"] = r
+    out["kept_mean"] = float(ws.det.count.float().mean())
+    # CPU oracle on a sub-sample, scaled (flagged)
+    from oracle import head as ohead
+    from oracle import nms as onms
+    h = head[:cpu_images].cpu()
+    t0 = time.perf_counter()
+    pred = ohead.detect_inference_ref(h, lv)
+    t1 = time.perf_counter()
+    onms.non_max_suppression_ref(pred, 0.001, 0.7, max_det=300)
+    t2 = time.perf_counter()
+    out["cpu_oracle"] = {"images": cpu_images, "decode_ms_per_image": 1e3 * (t1 - t0) / cpu_images,
+                         "nms_ms_per_image": 1e3 * (t2 - t1) / cpu_images, "cores": os.cpu_count(),
+                         "note": f"sub-sample of {cpu_images} images, per-image figures (not scaled to B)"}
+    return out
+
+
+def config4(dev, N=4096, B=64):
+    frames = synth.synth_frames(B, 1200, 1920, seed=0).to(dev)
+    boxes, bidx = synth.synth_rois(N, B, seed=0)
+    boxes, bidx = boxes.to(dev), bidx.to(dev)
+    dst = torch.empty((N, 3, 64, 64), dtype=torch.float32, device=dev)
+    valid = torch.empty((N,), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    r = timed(lambda: m.crop_resize_rois(frames, boxes, bidx, pad=6, out=dst, valid=valid), flush=flush)
+    from oracle import boxes as oboxes
+    crop_bytes = 0
+    for i in range(N):
+        c = oboxes.safe_crop_box_ref((1200, 1920), *[int(v) for v in boxes[i].cpu()], pad=6)
+        crop_bytes += (c[2] - c[0]) * (c[3] - c[1]) * 3
+    algo = crop_bytes + N * 49152
+    r.update(rois=N, rois_per_s=N / (r["us_median"] * 1e-6), algorithmic_bytes=algo,
+             algo_GBps=algo / (r["us_median"] * 1e-6) / 1e9, l2="L2 flushed between iterations")
+    return r
+
+
+def config1(dev):
+    out = {}
+    frame = synth.synth_frames(1, 900, 1600, seed=0)
+    for auto in (False, True):
+        pipe = m.Pipeline(1, (900, 1600), 64, imgsz=640, auto=auto, conf=0.25, iou=0.45, device=dev)
+        head, _ = synth.synth_head_from_labels(1, 64, in_hw=pipe.in_hw, src_hw=(900, 1600), seed=0)
+        f, h = frame.to(dev), head.to(dev)
+        eager = timed(lambda: pipe(f, h), iters=20)
+        pipe.capture(f, h)
+        graph = timed(lambda: pipe.replay(), iters=20)
+        out[f"auto={auto}"] = {"in_hw": list(pipe.in_hw), "anchors": pipe.A, "eager": eager, "cuda_graph": graph,
+                               "detections": int(pipe.ws.det.count[0])}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_extra.json"))
+    ap.add_argument("--b3", type=int, default=256)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    res = {"config3_nms_heavy": config3(dev, B=args.b3), "config4_roi_4096": config4(dev),
+           "config1_single_frame": config1(dev)}
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(res, open(args.out, "w"), indent=1)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

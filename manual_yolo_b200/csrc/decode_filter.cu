@@ -5,12 +5,15 @@
 // ops.non_max_suppression (amax > conf, xywh2xyxy, cls.max, conf filter, classes filter) -- reference
 // entry detect.py:541 / yolo.py:361 / pipe.py:179.  Restated in oracle/head.py + oracle/nms.py.
 //
-// One thread per anchor.  The head is channel-major with the anchor axis contiguous, so a warp's
-// load of one channel is one coalesced 128-byte line; channels are streamed with an unrolled loop
-// (16 independent loads in flight per thread).  Work is lazy: the class channels are reduced to the
-// best logit first, only anchors whose best sigmoid beats conf_thres (about 1% at conf 0.25, all of
-// them at conf 0.001) read and decode the 64 DFL channels.  Survivors are compacted with a warp
-// ballot and one atomicAdd per warp on the per-image counter.
+// A CTA of 8 warps covers 64 consecutive anchors: two groups of 4 warps, each group owning 32 anchors
+// (lane = anchor, so every channel load is one coalesced 128-byte line).  Within a group the channel
+// axis is split four ways: warp q reduces class channels [q*nc/4, (q+1)*nc/4) -- all of a thread's loads
+// are independent and issued in ONE round (16 in flight for nc=64) -- and the partial (max, argmax)
+// pairs are merged through shared memory in class order (first-maximum semantics of cls.max(1)).
+// Work is lazy: only if some anchor of the CTA beats conf_thres (about 1% of anchors at conf 0.25, all of
+// them at conf 0.001) do the four warps of a group decode the four box sides (warp q = side q: 16 DFL
+// bins, softmax expectation), again one load round.  Survivors are compacted with a warp ballot and one
+// atomicAdd per group on the per-image counter.
 // HBM-bound: algorithmic bytes per frame = (64+nc)*A*4 read + 28 B per survivor written.
 // Compiled with -fmad=false: every add/mul below rounds separately, as the torch CPU ops do.
 
@@ -31,7 +34,6 @@ struct Levels {
   int n;
 };
 
-__device__ __forceinline__ float sigmoid_f32(float x) { return b200::sigmoid_torch(x); }
 
 __device__ __forceinline__ bool class_allowed(const uint32_t* mask, int c) {
   return mask == nullptr || ((mask[c >> 5] >> (c & 31)) & 1u);
@@ -59,36 +61,56 @@ __device__ __forceinline__ void emit(bool is_cand, int b, int a, float x1, float
   }
 }
 
-__global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L, int nc, float conf,
+constexpr int kQ = 4;                       // warps per anchor group (channel quarters / box sides)
+constexpr int kGroups = kThreads / 32 / kQ; // anchor groups per CTA (2)
+constexpr int kAnchorsPerCta = kGroups * 32;
+
+struct Part { float m, m2; int j; };
+
+// RAW = true : head (B, 64+nc, A) per level -> DFL decode;  RAW = false: decoded prediction (B, ch, A).
+template <bool RAW>
+__global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L, const float* __restrict__ pred,
+                                                                 int channels, int nc, float conf,
                                                                  const uint32_t* __restrict__ class_mask,
                                                                  float* __restrict__ cand,
                                                                  int* __restrict__ cand_anchor,
                                                                  int* __restrict__ cand_count, int cap) {
+  __shared__ Part part[kGroups][kQ][32];
+  __shared__ float dist[kGroups][kQ][32];
+  __shared__ unsigned char flag[kGroups][32];
   const int A = L.off[B200YOLO_MAX_LEVELS];
-  const int a = blockIdx.x * kThreads + threadIdx.x;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = wid / kQ, q = wid % kQ;
+  const int a = (blockIdx.x * kGroups + g) * 32 + lane;
   const int b = blockIdx.y;
   const bool live = a < A;
-  // level lookup with static indices only (dynamic indexing would spill the params to local memory)
+  // per-lane level lookup with static indices only (dynamic indexing would spill the params)
   int off = 0, lw = L.w[0];
   long long cs = L.cstride[0], bs = L.bstride[0];
   const float* base = L.ptr[0];
   float st = L.stride[0];
+  if (RAW) {
 #pragma unroll
-  for (int l = 1; l < B200YOLO_MAX_LEVELS; ++l) {
-    if (l < L.n && a >= L.off[l]) {
-      off = L.off[l]; lw = L.w[l]; cs = L.cstride[l]; bs = L.bstride[l]; base = L.ptr[l]; st = L.stride[l];
+    for (int l = 1; l < B200YOLO_MAX_LEVELS; ++l) {
+      if (l < L.n && a >= L.off[l]) {
+        off = L.off[l]; lw = L.w[l]; cs = L.cstride[l]; bs = L.bstride[l]; base = L.ptr[l]; st = L.stride[l];
+      }
     }
+  } else {
+    cs = A; bs = (long long)channels * A; base = pred;
   }
   const int i = live ? a - off : 0;
   const float* p = base + (long long)b * bs + i;
+  const float* pc = p + (long long)(RAW ? 4 * kReg : 4) * cs;   // first class channel
 
-  // ---- class channels: best logit m (first index j), and m2 = best logit among indices < j ----
+  // ---- phase 1: this warp's quarter of the class channels, one load round ----
+  const int cq = (nc + kQ - 1) / kQ;
+  const int c0 = q * cq, c1 = min(nc, c0 + cq);
   float m = -INFINITY, m2 = -INFINITY;
-  int j = 0;
+  int j = c0;
   if (live) {
-    const float* pc = p + (long long)(4 * kReg) * cs;
-    int c = 0;
-    for (; c + 16 <= nc; c += 16) {
+    int c = c0;
+    for (; c + 16 <= c1; c += 16) {
       float v[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) v[u] = b200::ldg_stream(pc + (long long)(c + u) * cs);
@@ -96,95 +118,83 @@ __global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L,
       for (int u = 0; u < 16; ++u)
         if (v[u] > m) { m2 = m; m = v[u]; j = c + u; }
     }
-    for (; c < nc; ++c) {
-      float v = b200::ldg_stream(pc + (long long)c * cs);
-      if (v > m) { m2 = m; m = v; j = c; }
+    if (c < c1) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (c + u < c1) ? b200::ldg_stream(pc + (long long)(c + u) * cs) : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (v[u] > m) { m2 = m; m = v[u]; j = c + u; }
     }
   }
-  const float score = sigmoid_f32(m);
-  bool is_cand = live && (score > conf);
+  part[g][q][lane] = Part{m, m2, j};
+  __syncthreads();
+
+  // ---- phase 2: merge quarters in class order (first maximum wins), threshold, class filter ----
+  float score = 0.f;
+  int cls = 0;
+  bool is_cand = false;
+  if (q == 0) {
+    Part t = part[g][0][lane];
+    m = t.m; m2 = t.m2; j = t.j;
+#pragma unroll
+    for (int k = 1; k < kQ; ++k) {
+      t = part[g][k][lane];
+      if (t.m > m) { m2 = fmaxf(m, t.m2); m = t.m; j = t.j; }   // everything before t.j: earlier quarters + t.m2
+    }
+    score = RAW ? b200::sigmoid_torch(m) : m;
+    is_cand = live && (score > conf);
+    cls = j;
+    if (RAW && is_cand && m2 > -INFINITY && b200::sigmoid_torch(m2) == score) {
+      // cls.max(1) returns the LOWEST index whose sigmoid equals the maximum: an earlier class with a
+      // smaller logit can still tie after rounding/saturation (practically never: rescan is rare).
+      for (int c = 0; c < j; ++c)
+        if (b200::sigmoid_torch(pc[(long long)c * cs]) == score) { cls = c; break; }
+    }
+    if (is_cand && !class_allowed(class_mask, cls)) is_cand = false;
+    flag[g][lane] = is_cand;
+  }
+  if (!__syncthreads_or(is_cand)) return;   // no survivor among this CTA's 64 anchors (the common case)
 
   float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-  if (is_cand) {
-    // cls.max(1) returns the LOWEST index whose sigmoid equals the maximum: an earlier class with a
-    // smaller logit can still tie after rounding/saturation.  m2 bounds every earlier logit, so the
-    // rescan is needed only when sigmoid(m2) == sigmoid(m) (practically never).
-    if (m2 > -INFINITY && sigmoid_f32(m2) == score) {
-      const float* pc = p + (long long)(4 * kReg) * cs;
-      for (int c = 0; c < j; ++c) {
-        if (sigmoid_f32(pc[(long long)c * cs]) == score) { j = c; break; }
-      }
-    }
-    if (!class_allowed(class_mask, j)) is_cand = false;
-  }
-  if (is_cand) {
-    // ---- DFL: softmax over 16 bins per side, expectation with weights 0..15 (sequential) ----
-    float d[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
+  if (RAW) {
+    // ---- phase 3: warp q decodes box side q for the group's surviving lanes (DFL expectation) ----
+    if (flag[g][lane]) {
       float v[kReg];
 #pragma unroll
-      for (int k = 0; k < kReg; ++k) v[k] = p[(long long)(s * kReg + k) * cs];
+      for (int k = 0; k < kReg; ++k) v[k] = p[(long long)(q * kReg + k) * cs];
       float mx = v[0];
 #pragma unroll
       for (int k = 1; k < kReg; ++k) mx = fmaxf(mx, v[k]);
       float sum = 0.f;
 #pragma unroll
       for (int k = 0; k < kReg; ++k) { v[k] = b200::expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
-      float acc = 0.f;
+      float acc = 0.f;   // torch's 1x1 conv with arange weights: sequential fma over the 16 bins
 #pragma unroll
       for (int k = 0; k < kReg; ++k) acc = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), acc);
-      d[s] = acc;
+      dist[g][q][lane] = acc;
     }
-    // ---- dist2bbox(xywh=True) * stride, then xywh2xyxy, in the reference's op order ----
-    const int w = lw;
-    const float ax = (float)(i % w) + 0.5f, ay = (float)(i / w) + 0.5f;
-    const float bx1 = ax - d[0], by1 = ay - d[1], bx2 = ax + d[2], by2 = ay + d[3];
-    const float cx = ((bx1 + bx2) / 2.0f) * st, cy = ((by1 + by2) / 2.0f) * st;
-    const float bw = (bx2 - bx1) * st, bh = (by2 - by1) * st;
-    const float hw = bw / 2.0f, hh = bh / 2.0f;
-    x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
-  }
-  emit(is_cand, b, a, x1, y1, x2, y2, score, j, cand, cand_anchor, cand_count, cap);
-}
-
-// Already-decoded UL prediction (B, channels, A): rows 0-3 xywh, rows 4..4+nc scores.
-__global__ void __launch_bounds__(kThreads) filter_decoded_kernel(const float* __restrict__ pred, int channels,
-                                                                  int nc, int A, float conf,
-                                                                  const uint32_t* __restrict__ class_mask,
-                                                                  float* __restrict__ cand,
-                                                                  int* __restrict__ cand_anchor,
-                                                                  int* __restrict__ cand_count, int cap) {
-  const int a = blockIdx.x * kThreads + threadIdx.x;
-  const int b = blockIdx.y;
-  const bool live = a < A;
-  const float* p = pred + ((long long)b * channels) * A + a;
-  float m = -INFINITY;
-  int j = 0;
-  if (live) {
-    const float* pc = p + 4LL * A;
-    int c = 0;
-    for (; c + 16 <= nc; c += 16) {
-      float v[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = b200::ldg_stream(pc + (long long)(c + u) * A);
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (v[u] > m) { m = v[u]; j = c + u; }
+    __syncthreads();
+    if (q != 0) return;
+    if (is_cand) {
+      // dist2bbox(xywh=True) * stride, then xywh2xyxy, in the reference's op order
+      const float d0 = dist[g][0][lane], d1 = dist[g][1][lane], d2 = dist[g][2][lane], d3 = dist[g][3][lane];
+      const float ax = (float)(i % lw) + 0.5f, ay = (float)(i / lw) + 0.5f;
+      const float bx1 = ax - d0, by1 = ay - d1, bx2 = ax + d2, by2 = ay + d3;
+      const float cx = ((bx1 + bx2) / 2.0f) * st, cy = ((by1 + by2) / 2.0f) * st;
+      const float bw = (bx2 - bx1) * st, bh = (by2 - by1) * st;
+      const float hw = bw / 2.0f, hh = bh / 2.0f;
+      x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
     }
-    for (; c < nc; ++c) {
-      float v = b200::ldg_stream(pc + (long long)c * A);
-      if (v > m) { m = v; j = c; }
+  } else {
+    if (q != 0) return;
+    if (is_cand) {
+      const float cx = p[0], cy = p[cs], bw = p[2 * cs], bh = p[3 * cs];
+      const float hw = bw / 2.0f, hh = bh / 2.0f;
+      x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
     }
   }
-  bool is_cand = live && (m > conf) && class_allowed(class_mask, j);
-  float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-  if (is_cand) {
-    const float cx = p[0], cy = p[A], bw = p[2LL * A], bh = p[3LL * A];
-    const float hw = bw / 2.0f, hh = bh / 2.0f;
-    x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
-  }
-  emit(is_cand, b, a, x1, y1, x2, y2, m, j, cand, cand_anchor, cand_count, cap);
+  emit(is_cand, b, a, x1, y1, x2, y2, score, cls, cand, cand_anchor, cand_count, cap);
 }
 
 }  // namespace
@@ -214,9 +224,9 @@ extern "C" int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels
   }
   B200_REQUIRE(off <= (1LL << 30), B200YOLO_ERR_UNSUPPORTED);
   for (int l = n_levels; l <= B200YOLO_MAX_LEVELS; ++l) L.off[l] = (int)off;
-  dim3 grid((unsigned)((off + kThreads - 1) / kThreads), B);
-  decode_filter_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, nc, conf_thres, class_mask, cand,
-                                                                     cand_anchor, cand_count, cap);
+  dim3 grid((unsigned)((off + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
+  decode_filter_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, nullptr, 0, nc, conf_thres, class_mask,
+                                                                           cand, cand_anchor, cand_count, cap);
   return b200_launch_status();
 }
 
@@ -228,9 +238,16 @@ extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, i
   B200_REQUIRE(nc <= B200YOLO_MAX_CLASSES, B200YOLO_ERR_UNSUPPORTED);
   B200_REQUIRE(conf_thres >= 0.f && conf_thres <= 1.f, B200YOLO_ERR_RANGE);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(pred) & 3) == 0, B200YOLO_ERR_ALIGN);
-  dim3 grid((unsigned)((A + kThreads - 1) / kThreads), B);
-  filter_decoded_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(pred, channels, nc, A, conf_thres,
-                                                                      class_mask, cand, cand_anchor, cand_count,
-                                                                      cap);
+  Levels L;
+  L.n = 1;
+  for (int l = 0; l < B200YOLO_MAX_LEVELS; ++l) {
+    L.ptr[l] = pred; L.bstride[l] = (long long)channels * A; L.cstride[l] = A; L.w[l] = 1; L.stride[l] = 1.f;
+    L.off[l] = l == 0 ? 0 : A;
+  }
+  L.off[B200YOLO_MAX_LEVELS] = A;
+  dim3 grid((unsigned)((A + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
+  decode_filter_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, pred, channels, nc, conf_thres,
+                                                                            class_mask, cand, cand_anchor, cand_count,
+                                                                            cap);
   return b200_launch_status();
 }

@@ -4,12 +4,15 @@
 // detect.py:541, yolo.py:361, pipe.py:179); arithmetic restated in oracle/letterbox.py
 // (SURVEY.md Appendix B.1).
 //
-// One CTA produces one output row of one frame.  The (at most two) source rows the bilinear taps
-// reference are staged in shared memory by the TMA engine (cp.async.bulk, 1-D, mbarrier
-// completion) when the row is 16-byte aligned, else by cooperative loads; while the copy is in
-// flight every thread derives its own horizontal taps (double/float arithmetic exactly as
-// cv::resize builds its tables).  Each thread then emits 4 output pixels: three 128-bit streaming
-// stores into the planar fp32 image (or 12 interleaved bytes for the u8 variant).
+// One CTA produces kRows consecutive output rows of one frame; thread t owns output pixels 4t..4t+3 of
+// every row, so its horizontal taps (double/float arithmetic exactly as cv::resize builds its tables)
+// are derived ONCE and stay in registers.  The (at most two) source rows each output row references are
+// staged in shared memory by the TMA engine (cp.async.bulk 1-D copies completing on an mbarrier;
+// SASS UBLKCP) into a two-stage ring: row r+1 is in flight while row r is blended.  Rows that are not
+// 16-byte aligned fall back to cooperative loads.  Per pixel: three 32-bit LDS + funnel shifts fetch the
+// two BGR taps, cv2's fixed-point blend (or a pass-through when the scale is an exact integer and the
+// weights degenerate to 2048/0), an exact u8 -> v/255 table lookup, three 128-bit streaming stores
+// (planar RGB) -- or 12 interleaved bytes for the u8 variant.
 // HBM-bound: algorithmic bytes per frame = referenced rows * W*3 + 3*outH*outW*4.
 
 #include "common.cuh"
@@ -61,11 +64,11 @@ __device__ __forceinline__ void load6(const uint8_t* row, int off, uint32_t& lo,
 }
 
 template <typename OutT>
-__device__ __forceinline__ OutT lb_cast(int v);
+__device__ __forceinline__ OutT lb_cast(const float* lut, int v);
 template <>
-__device__ __forceinline__ float lb_cast<float>(int v) { return b200::u8_div255(v); }
+__device__ __forceinline__ float lb_cast<float>(const float* lut, int v) { return lut[v]; }   // exact v/255 table
 template <>
-__device__ __forceinline__ uint8_t lb_cast<uint8_t>(int v) { return (uint8_t)v; }
+__device__ __forceinline__ uint8_t lb_cast<uint8_t>(const float*, int v) { return (uint8_t)v; }
 
 template <typename OutT>
 __device__ __forceinline__ void store_px4(const LbParams& p, int b, int oy, int ox, const OutT (&v)[4][3], int n) {
@@ -96,92 +99,142 @@ __device__ __forceinline__ void store_px4(const LbParams& p, int b, int oy, int 
   }
 }
 
+constexpr int kRows = 8;     // output rows per CTA
+constexpr int kStages = 2;
+
 template <typename OutT>
-__global__ void __launch_bounds__(256) letterbox_kernel(const LbParams p) {
+__global__ void __launch_bounds__(256, 5) letterbox_kernel(const LbParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
-  const int oy = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const OutT padv = lb_cast<OutT>(p.pad_value);
+  __shared__ __align__(8) uint64_t bar[kStages];
+  __shared__ float lut[256];
+  __shared__ int span[2];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int oy0 = blockIdx.x * kRows;
+  const int nrows = min(kRows, p.outH - oy0);
+  const int ox_base = blockIdx.z * (int)blockDim.x * 4;          // this CTA's column chunk
+  const int ox0 = ox_base + tid * 4;
+  const bool have = ox0 < p.outW;
 
-  const bool interior = (oy >= p.top) && (oy < p.top + p.new_h);
-  int sy = 0, sy1 = 0, b0 = 2048, b1 = 0;
-  if (interior) cv_linear_tap_v(oy - p.top, p.scale_y, p.H, sy, sy1, b0, b1);
-  const bool two_rows = interior && (b1 != 0);
-  const bool load_row1 = two_rows && (sy1 != sy);
-  uint8_t* row0 = smem;
-  uint8_t* row1 = load_row1 ? smem + p.row_smem : smem;   // clamped rows alias the same staged row
-
-  if (interior) {
-    const uint8_t* g0 = p.src + (int64_t)b * p.bstride + (int64_t)sy * p.pitch;
-    const uint8_t* g1 = p.src + (int64_t)b * p.bstride + (int64_t)sy1 * p.pitch;
+  for (int v = tid; v < 256; v += blockDim.x) lut[v] = b200::u8_div255(v);
+  if (tid == 0) {
     if (p.bulk_ok) {
-      if (tid == 0) {
-        b200::mbar_init(&bar, 1);
-        b200::mbar_fence_init();
-        b200::mbar_expect_tx(&bar, load_row1 ? 2u * p.row_bytes : (uint32_t)p.row_bytes);
-        b200::bulk_g2s(row0, g0, p.row_bytes, &bar);
-        if (load_row1) b200::bulk_g2s(row1, g1, p.row_bytes, &bar);
-      }
-    } else {
-      for (int i = tid; i < p.row_bytes; i += blockDim.x) {
-        row0[i] = g0[i];
-        if (load_row1) row1[i] = g1[i];
-      }
+      for (int s = 0; s < kStages; ++s) b200::mbar_init(&bar[s], 1);
+      b200::mbar_fence_init();
     }
+    // byte span of a source row this chunk's columns reference (16-byte granular)
+    const int lo_ox = max(ox_base, p.left);
+    const int hi_ox = min(min(ox_base + (int)blockDim.x * 4, p.outW), p.left + p.new_w) - 1;
+    int blo = 0, bhi = 0;
+    if (lo_ox <= hi_ox) {
+      int s_lo, s_hi, t0, t1;
+      cv_linear_tap(lo_ox - p.left, p.scale_x, p.W, s_lo, t0, t1);
+      cv_linear_tap(hi_ox - p.left, p.scale_x, p.W, s_hi, t0, t1);
+      blo = (s_lo * 3) & ~15;
+      bhi = min(p.row_bytes, ((min(s_hi + 2, p.W) * 3) + 15) & ~15);
+      if (!p.bulk_ok) bhi = min(s_hi + 2, p.W) * 3;
+    }
+    span[0] = blo; span[1] = bhi;
   }
-
-  // horizontal taps of this thread's first pixel group are derived while the copy is in flight
-  const int groups = (p.outW + 3) >> 2;
-  int g = tid;
-  bool have = g < groups;
+  // horizontal taps of this thread's 4 pixels: derived once, kept in registers for all kRows rows
   int sx[4], a0[4], a1[4];
   bool in[4];
-  auto taps = [&](int grp) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int ox = grp * 4 + k;
-      in[k] = interior && (ox >= p.left) && (ox < p.left + p.new_w);
-      sx[k] = 0; a0[k] = 0; a1[k] = 0;
-      if (in[k]) cv_linear_tap(ox - p.left, p.scale_x, p.W, sx[k], a0[k], a1[k]);
+  for (int k = 0; k < 4; ++k) {
+    const int ox = ox0 + k;
+    in[k] = have && (ox >= p.left) && (ox < p.left + p.new_w);
+    sx[k] = 0; a0[k] = 2048; a1[k] = 0;
+    if (in[k]) cv_linear_tap(ox - p.left, p.scale_x, p.W, sx[k], a0[k], a1[k]);
+  }
+  __syncthreads();
+  const int blo = span[0], nbytes = span[1] - span[0];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sx[k] = sx[k] * 3 - blo;            // byte offset inside the staged span
+
+  const uint8_t* frame = p.src + (int64_t)b * p.bstride + blo;
+  // vertical taps of output row oy (CTA-uniform)
+  auto row_taps = [&](int oy, int& r0, int& r1, int& b0, int& b1) -> bool {
+    const bool interior = (oy >= p.top) && (oy < p.top + p.new_h) && nbytes > 0;
+    r0 = r1 = 0; b0 = 2048; b1 = 0;
+    if (interior) cv_linear_tap_v(oy - p.top, p.scale_y, p.H, r0, r1, b0, b1);
+    return interior;
+  };
+  // stage the source rows of output row `oy` into ring slot `s`
+  auto prefetch = [&](int oy, int s) {
+    int r0, r1, b0, b1;
+    if (!row_taps(oy, r0, r1, b0, b1)) return;
+    const bool need1 = (b1 != 0) && (r1 != r0);
+    uint8_t* d0 = smem + (size_t)s * 2 * p.row_smem;
+    uint8_t* d1 = d0 + p.row_smem;
+    const uint8_t* g0 = frame + (int64_t)r0 * p.pitch;
+    const uint8_t* g1 = frame + (int64_t)r1 * p.pitch;
+    if (p.bulk_ok) {
+      if (tid == 0) {
+        b200::mbar_expect_tx(&bar[s], need1 ? 2u * nbytes : (uint32_t)nbytes);
+        b200::bulk_g2s(d0, g0, nbytes, &bar[s]);
+        if (need1) b200::bulk_g2s(d1, g1, nbytes, &bar[s]);
+      }
+    } else {
+      for (int i = tid; i < nbytes; i += blockDim.x) {
+        d0[i] = g0[i];
+        if (need1) d1[i] = g1[i];
+      }
     }
   };
-  if (have) taps(g);
-  if (interior) {          // CTA-uniform
-    __syncthreads();       // staged rows (fallback path) / mbarrier init (bulk path) visible
-    if (p.bulk_ok) b200::mbar_wait(&bar, 0);
-  }
-  while (have) {
-    const int ox0 = g * 4;
-    const int n = min(4, p.outW - ox0);
-    OutT v[4][3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!in[k]) {
-        v[k][0] = v[k][1] = v[k][2] = padv;
-        continue;
-      }
-      uint32_t lo, hi;
-      load6(row0, sx[k] * 3, lo, hi);
-      int S0[3], S1[3] = {0, 0, 0};
-      S0[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
-      S0[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
-      S0[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
-      if (two_rows) {
-        load6(row1, sx[k] * 3, lo, hi);
-        S1[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
-        S1[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
-        S1[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        int r = (((b0 * (S0[c] >> 4)) >> 16) + ((b1 * (S1[c] >> 4)) >> 16) + 2) >> 2;
-        v[k][c] = lb_cast<OutT>(r);
+
+  prefetch(oy0, 0);
+  const OutT padv = lb_cast<OutT>(lut, p.pad_value);
+  int uses[kStages] = {0, 0};                        // completed phases per ring slot (only interior rows arm it)
+  for (int r = 0; r < nrows; ++r) {
+    const int oy = oy0 + r, s = r & 1;
+    int r0, r1, b0, b1;
+    const bool interior = row_taps(oy, r0, r1, b0, b1);
+    if (r + 1 < nrows) prefetch(oy + 1, s ^ 1);      // slot s^1 was released by the barrier ending row r-1
+    if (interior) {
+      if (p.bulk_ok) {
+        if (s == 0) { b200::mbar_wait(&bar[0], uses[0] & 1); ++uses[0]; }
+        else { b200::mbar_wait(&bar[1], uses[1] & 1); ++uses[1]; }
+      } else {
+        __syncthreads();
       }
     }
-    store_px4<OutT>(p, b, oy, ox0, v, n);
-    g += blockDim.x;
-    have = g < groups;
-    if (have) taps(g);
+    const uint8_t* row0 = smem + (size_t)s * 2 * p.row_smem;
+    const uint8_t* row1 = ((b1 != 0) && (r1 != r0)) ? row0 + p.row_smem : row0;
+    const bool pass_v = (b1 == 0) && (b0 == 2048);
+    if (have) {
+      OutT v[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!(interior && in[k])) {
+          v[k][0] = v[k][1] = v[k][2] = padv;
+          continue;
+        }
+        uint32_t lo, hi;
+        load6(row0, sx[k], lo, hi);
+        if (pass_v && a1[k] == 0 && a0[k] == 2048) {       // exact integer decimation: the source pixel itself
+          v[k][0] = lb_cast<OutT>(lut, (int)(lo & 0xff));
+          v[k][1] = lb_cast<OutT>(lut, (int)((lo >> 8) & 0xff));
+          v[k][2] = lb_cast<OutT>(lut, (int)((lo >> 16) & 0xff));
+          continue;
+        }
+        int S0[3], S1[3] = {0, 0, 0};
+        S0[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
+        S0[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
+        S0[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
+        if (b1 != 0) {
+          load6(row1, sx[k], lo, hi);
+          S1[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
+          S1[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
+          S1[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int q = (((b0 * (S0[c] >> 4)) >> 16) + ((b1 * (S1[c] >> 4)) >> 16) + 2) >> 2;
+          v[k][c] = lb_cast<OutT>(lut, q);
+        }
+      }
+      store_px4<OutT>(p, b, oy, ox0, v, min(4, p.outW - ox0));
+    }
+    __syncthreads();   // every thread is done with ring slot s: it may be refilled for row r+2
   }
 }
 
@@ -203,10 +256,10 @@ int launch_letterbox(const uint8_t* src, int B, int H, int W, int64_t pitch, int
   p.scale_x = 1.0 / ((double)new_w / (double)W);
   p.scale_y = 1.0 / ((double)new_h / (double)H);
   p.row_bytes = W * 3;
-  p.row_smem = ((p.row_bytes + 15) / 16) * 16 + 16;
+  p.row_smem = ((p.row_bytes + 15) / 16) * 16 + 32;
   p.bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (pitch % 16 == 0) && (bstride % 16 == 0) &&
               (p.row_bytes % 16 == 0);
-  const size_t smem = 2 * (size_t)p.row_smem;
+  const size_t smem = (size_t)kStages * 2 * (size_t)p.row_smem;
   B200_REQUIRE(smem <= 200 * 1024, B200YOLO_ERR_UNSUPPORTED);
   auto kern = letterbox_kernel<OutT>;
   if (smem > 48 * 1024) {
@@ -214,9 +267,9 @@ int launch_letterbox(const uint8_t* src, int B, int H, int W, int64_t pitch, int
     if (e != cudaSuccess) return (int)e;
   }
   int groups = (outW + 3) / 4;
-  int threads = ((groups + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  dim3 grid(outH, B);
+  int chunks = (groups + 255) / 256;                 // column chunks (grid.z): one pixel group per thread
+  int threads = (((groups + chunks - 1) / chunks + 31) / 32) * 32;
+  dim3 grid((outH + kRows - 1) / kRows, B, chunks);
   kern<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
   return b200_launch_status();
 }

@@ -20,19 +20,16 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kMaxSize = 64;     // output side supported by the shared-memory plan
+constexpr int kS = 64;           // output side (the rank classifier's imgsz; class.py:26, args.yaml imgsz: 64)
+constexpr int kThreads = 3 * kS; // one thread per (channel, output column)
 constexpr int kMaxTaps = 64;     // ksize = ceil(support)*2+1 <= 64  <=> scale <= 31
-constexpr int kRowsMax = 192;    // uint8 strip rows staged per vertical tile
+constexpr int kFastTaps = 8;     // taps kept in registers (scale <= 3.5: every rank-card crop)
+constexpr int kRowsMax = 128;    // uint8 strip rows staged per vertical tile (>= kMaxTaps)
 constexpr int kPrec = 22;        // Pillow PRECISION_BITS = 32 - 8 - 2
 
-struct AxisPlan {
-  int bounds[kMaxSize][2];          // xmin, count
-  int coef[kMaxSize][kMaxTaps];
-};
-
-// Pillow precompute_coeffs + normalize_coeffs_8bpc for output index `o` (triangle filter).
-__device__ void pil_axis(int o, int in_size, int out_size, int* bounds, int* coef) {
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for output index `o` (triangle filter):
+// returns xmin, writes `cnt` fixed-point weights.
+__device__ int pil_axis(int o, int in_size, int out_size, int* coef, int& cnt_out) {
   const double scale = __ddiv_rn((double)in_size, (double)out_size);
   const double fscale = scale < 1.0 ? 1.0 : scale;
   const double support = fscale;  // bilinear support 1.0 * filterscale
@@ -58,8 +55,8 @@ __device__ void pil_axis(int o, int in_size, int out_size, int* bounds, int* coe
     if (ww != 0.0) w = __ddiv_rn(w, ww);
     coef[x] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrec))));
   }
-  bounds[0] = xmin;
-  bounds[1] = xmax;
+  cnt_out = xmax;
+  return xmin;
 }
 
 __device__ __forceinline__ int clip8(int v) {
@@ -73,112 +70,103 @@ __device__ __forceinline__ int half_round_even(int d) {
   return (d & 1) ? ((k & 1) ? k + 1 : k) : k;
 }
 
-// Word load that never touches bytes outside [lo, hi) (the caller's frame buffer).
-__device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* a, const uint8_t* lo, const uint8_t* hi) {
-  if (a >= lo && a + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(a));
-  uint32_t w = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (a + k >= lo && a + k < hi) w |= (uint32_t)__ldg(a + k) << (8 * k);
-  return w;
-}
-
 struct RoiSmem {
-  AxisPlan px, py;
-  uint8_t strip[kRowsMax][kMaxSize][3];
+  int xb[kS][2];                 // horizontal bounds (xmin, count) per surviving output column
+  int yb[kS][2];                 // vertical bounds per surviving output row
+  int xk[kS][kFastTaps];         // horizontal weights, fast path (count <= kFastTaps)
+  int yk[kS][kMaxTaps];          // vertical weights (broadcast reads)
+  uint8_t strip[kRowsMax][3][kS];  // horizontal-pass output, uint8 like Pillow's intermediate image
   int sel[4];
 };
-constexpr int kStageBytes = 64 * 1024;   // staged crop rows (typical rank crop: ~36 KB)
 
-// One ROI per CTA.  (bi, x1..y2) already int()-truncated box in source pixels.
-__device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_lo, const uint8_t* buf_hi, int B, int H,
-                         int W, int64_t pitch, int64_t bstride, int bi, int bx1, int by1, int bx2, int by2, int pad, int S,
-                         float* __restrict__ out, int* __restrict__ valid_out, RoiSmem& sm, uint8_t* stage) {
+// One ROI per CTA, one thread per (channel c, output column xx).  (bi, x1..y2): already int()-truncated
+// box in source pixels.
+__device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
+                         int bi, int bx1, int by1, int bx2, int by2, int pad, float* __restrict__ out,
+                         int* __restrict__ valid_out, RoiSmem& sm) {
   const int tid = threadIdx.x;
-  AxisPlan& px = sm.px;
-  AxisPlan& py = sm.py;
+  const int c = tid / kS, xx = tid % kS;       // warp = 32 consecutive columns of one channel
   // ---- safe_crop (detect.py:100-113) ----
   const int cx1 = max(0, min(W - 1, bx1 - pad)), cx2 = max(0, min(W, bx2 + pad));
   const int cy1 = max(0, min(H - 1, by1 - pad)), cy2 = max(0, min(H, by2 + pad));
   const int cw = cx2 - cx1, ch = cy2 - cy1;
   bool ok = (bi >= 0 && bi < B && cw > 0 && ch > 0), unsupported = false;
   // torchvision Resize(int): short side -> S, long side -> int(S * long / short)
-  int new_w = S, new_h = S;
+  int new_w = kS, new_h = kS;
   if (ok) {
-    if (cw <= ch) new_h = __double2int_rz(__ddiv_rn((double)(S * (int64_t)ch), (double)cw));
-    else new_w = __double2int_rz(__ddiv_rn((double)(S * (int64_t)cw), (double)ch));
-    // supported envelope of the shared-memory plan: ksize = ceil(support)*2+1 <= kMaxTaps on both axes
+    if (cw <= ch) new_h = __double2int_rz(__ddiv_rn((double)(kS * (int64_t)ch), (double)cw));
+    else new_w = __double2int_rz(__ddiv_rn((double)(kS * (int64_t)cw), (double)ch));
+    // supported envelope: ksize = ceil(support)*2+1 <= kMaxTaps on both axes
     const double sx = (double)cw / (double)new_w, sy = (double)ch / (double)new_h;
     const double smx = fmax(fmax(sx, sy), 1.0);
     if (2 * (int)ceil(smx) + 1 > kMaxTaps) { ok = false; unsupported = true; }
   }
   if (!ok) {
-    for (int i = tid; i < 3 * S * S; i += kThreads) out[i] = 0.f;
+    for (int i = tid; i < 3 * kS * kS; i += kThreads) out[i] = 0.f;
     if (tid == 0) *valid_out = unsupported ? -1 : 0;
     return;
   }
-  const int left = half_round_even(new_w - S), top = half_round_even(new_h - S);
+  const int left = half_round_even(new_w - kS), top = half_round_even(new_h - kS);
 
-  if (tid < S) pil_axis(left + tid, cw, new_w, px.bounds[tid], px.coef[tid]);
-  else if (tid >= 64 && tid < 64 + S) pil_axis(top + (tid - 64), ch, new_h, py.bounds[tid - 64], py.coef[tid - 64]);
+  // ---- coefficient tables: threads 0..63 horizontal (own column), 64..127 vertical ----
+  int kx_big[kMaxTaps];                         // only touched when a column has > kFastTaps taps (local mem)
+  if (tid < kS) {
+    int cnt;
+    const int xmin = pil_axis(left + tid, cw, new_w, kx_big, cnt);
+    sm.xb[tid][0] = xmin; sm.xb[tid][1] = cnt;
+    if (cnt <= kFastTaps)
+      for (int x = 0; x < kFastTaps; ++x) sm.xk[tid][x] = x < cnt ? kx_big[x] : 0;
+  } else if (tid < 2 * kS) {
+    int cnt;
+    const int ymin = pil_axis(top + (tid - kS), ch, new_h, sm.yk[tid - kS], cnt);
+    sm.yb[tid - kS][0] = ymin; sm.yb[tid - kS][1] = cnt;
+  }
   __syncthreads();
+  const int xmin = sm.xb[xx][0], xcnt = sm.xb[xx][1];
+  const bool fast_x = xcnt <= kFastTaps;
+  int kx[kFastTaps];
+#pragma unroll
+  for (int x = 0; x < kFastTaps; ++x) kx[x] = fast_x ? sm.xk[xx][x] : 0;
+  if (!fast_x && tid >= kS) {                   // big ROI: every thread of the column needs the long table
+    int cnt;
+    pil_axis(left + xx, cw, new_w, kx_big, cnt);
+  }
 
   const uint8_t* crop = frames + (int64_t)bi * bstride + (int64_t)cy1 * pitch + (int64_t)cx1 * 3;
-  // horizontal span of source columns the 64 surviving output columns reference
-  const int x_lo = px.bounds[0][0];
-  const int x_hi = px.bounds[S - 1][0] + px.bounds[S - 1][1];
-  const int span_bytes = (x_hi - x_lo) * 3;
-  const int row_words = (span_bytes + 3 + 3) / 4;          // any 4-byte phase fits
-  const int row_stride = row_words * 4;
+  const uint8_t* col = crop + (int64_t)xmin * 3 + c;
   int t0 = 0;
-  while (t0 < S) {
-    // vertical tile [t0, t1): input rows [rmin, rmax) must fit the strip (and, when staged, the stage)
-    const int rmin = py.bounds[t0][0];
-    const int rows_cap = min(kRowsMax, kStageBytes / row_stride);
-    const bool staged = rows_cap >= py.bounds[t0][1];
-    const int cap_rows = staged ? rows_cap : kRowsMax;
+  while (t0 < kS) {
+    // vertical tile [t0, t1): input rows [rmin, rmax) must fit the strip
+    const int rmin = sm.yb[t0][0];
     int t1 = t0 + 1;
-    while (t1 < S && py.bounds[t1][0] + py.bounds[t1][1] - rmin <= cap_rows) ++t1;
-    const int rmax = py.bounds[t1 - 1][0] + py.bounds[t1 - 1][1];
-    const int rows = rmax - rmin;
-    if (staged) {
-      // ---- stage the referenced crop rows: coalesced 4-byte loads, all in flight at once ----
-      for (int e = tid; e < rows * row_words; e += kThreads) {
-        const int rr = e / row_words, wd = e - rr * row_words;
-        const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
-        const uint8_t* ga = g - (reinterpret_cast<uintptr_t>(g) & 3) + wd * 4;
-        reinterpret_cast<uint32_t*>(stage + rr * row_stride)[wd] = load_word_guarded(ga, buf_lo, buf_hi);
-      }
-      __syncthreads();
-      for (int e = tid; e < rows * S * 3; e += kThreads) {
-        const int c = e % 3, xx = (e / 3) % S, rr = e / (3 * S);
-        const int xmin = px.bounds[xx][0], cnt = px.bounds[xx][1];
-        const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
-        const uint8_t* p = stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + (xmin - x_lo) * 3 + c;
+    while (t1 < kS && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kRowsMax) ++t1;
+    const int rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
+    // ---- horizontal pass: this thread's column for every referenced row ----
+    if (fast_x) {
+#pragma unroll 2
+      for (int rr = 0; rr < rows; ++rr) {
+        const uint8_t* p = col + (int64_t)(rmin + rr) * pitch;
         int acc = 1 << (kPrec - 1);
-        for (int x = 0; x < cnt; ++x) acc += (int)p[x * 3] * px.coef[xx][x];
-        sm.strip[rr][xx][c] = (uint8_t)clip8(acc);
+#pragma unroll
+        for (int x = 0; x < kFastTaps; ++x)
+          if (x < xcnt) acc += (int)__ldg(p + x * 3) * kx[x];
+        sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
       }
     } else {
-      // ---- oversize ROI: horizontal pass straight from global memory ----
-      for (int e = tid; e < rows * S * 3; e += kThreads) {
-        const int c = e % 3, xx = (e / 3) % S, rr = e / (3 * S);
-        const int xmin = px.bounds[xx][0], cnt = px.bounds[xx][1];
-        const uint8_t* p = crop + (int64_t)(rmin + rr) * pitch + xmin * 3 + c;
+      for (int rr = 0; rr < rows; ++rr) {
+        const uint8_t* p = col + (int64_t)(rmin + rr) * pitch;
         int acc = 1 << (kPrec - 1);
-        for (int x = 0; x < cnt; ++x) acc += (int)__ldg(p + x * 3) * px.coef[xx][x];
-        sm.strip[rr][xx][c] = (uint8_t)clip8(acc);
+        for (int x = 0; x < xcnt; ++x) acc += (int)__ldg(p + x * 3) * kx_big[x];
+        sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
       }
     }
     __syncthreads();
-    // ---- vertical pass + BGR->RGB + /255 ----
-    const int trows = t1 - t0;
-    for (int e = tid; e < 3 * trows * S; e += kThreads) {
-      const int xx = e % S, yy = t0 + (e / S) % trows, c = e / (S * trows);
-      const int ymin = py.bounds[yy][0], cnt = py.bounds[yy][1];
+    // ---- vertical pass + BGR->RGB + /255: coalesced 128-byte rows per warp ----
+    for (int yy = t0; yy < t1; ++yy) {
+      const int ymin = sm.yb[yy][0] - rmin, cnt = sm.yb[yy][1];
       int acc = 1 << (kPrec - 1);
-      for (int y = 0; y < cnt; ++y) acc += (int)sm.strip[ymin - rmin + y][xx][c] * py.coef[yy][y];
-      out[((2 - c) * S + yy) * S + xx] = b200::u8_div255(clip8(acc));
+      for (int y = 0; y < cnt; ++y) acc += (int)sm.strip[ymin + y][c][xx] * sm.yk[yy][y];
+      out[((2 - c) * kS + yy) * kS + xx] = b200::u8_div255(clip8(acc));
     }
     __syncthreads();
     t0 = t1;
@@ -187,37 +175,33 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
 }
 
 // ROI list form: boxes (N,4) float + batch_idx (N).
-__global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B,
-                                                       int H, int W, int64_t pitch, int64_t bstride,
+__global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
                                                        const float* __restrict__ boxes,
                                                        const int* __restrict__ batch_idx,
-                                                       const int* __restrict__ roi_count, int pad, int S,
+                                                       const int* __restrict__ roi_count, int pad,
                                                        float* __restrict__ dst, int* __restrict__ valid) {
   extern __shared__ __align__(16) uint8_t roi_smem[];
   RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
-  uint8_t* stage = roi_smem + ((sizeof(RoiSmem) + 15) & ~(size_t)15);
   const int r = blockIdx.x;
   if (roi_count != nullptr && r >= *roi_count) return;
   // int() truncation of the float box (detect.py:581)
-  roi_body(frames, frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
-           __float2int_rz(boxes[r * 4 + 1]), __float2int_rz(boxes[r * 4 + 2]), __float2int_rz(boxes[r * 4 + 3]), pad, S,
-           dst + (int64_t)r * 3 * S * S, valid + r, sm, stage);
+  roi_body(frames, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
+           __float2int_rz(boxes[r * 4 + 1]), __float2int_rz(boxes[r * 4 + 2]), __float2int_rz(boxes[r * 4 + 3]), pad,
+           dst + (int64_t)r * 3 * kS * kS, valid + r, sm);
 }
 
 // Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
 // the allow-list, from the per-image counts the NMS kernel wrote -- no separate selection launch.
-__global__ void __launch_bounds__(kThreads) roi_det_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi,
-                                                           int B, int H, int W, int64_t pitch, int64_t bstride,
+__global__ void __launch_bounds__(kThreads) roi_det_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
                                                            const float* __restrict__ det,
                                                            const int* __restrict__ det_count,
                                                            const int* __restrict__ roi_cnt, int max_det,
                                                            const uint32_t* __restrict__ class_mask, int nc, int pad,
-                                                           int S, float* __restrict__ dst, int* __restrict__ roi_batch,
+                                                           float* __restrict__ dst, int* __restrict__ roi_batch,
                                                            int* __restrict__ roi_det, int* __restrict__ valid,
                                                            int* __restrict__ roi_total, int roi_cap) {
   extern __shared__ __align__(16) uint8_t roi_smem[];
   RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
-  uint8_t* stage = roi_smem + ((sizeof(RoiSmem) + 15) & ~(size_t)15);
   __shared__ int wsum[kThreads / 32];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // ---- (1) which image: running prefix over roi_cnt[0..B) in chunks of kThreads ----
@@ -270,8 +254,8 @@ __global__ void __launch_bounds__(kThreads) roi_det_kernel(const uint8_t* __rest
   const int i = sm.sel[2];
   const float* row = det + ((int64_t)b * max_det + i) * 6;
   if (tid == 0) { roi_batch[g] = b; roi_det[g] = i; }
-  roi_body(frames, frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
-           __float2int_rz(row[2]), __float2int_rz(row[3]), pad, S, dst + (int64_t)g * 3 * S * S, valid + g, sm, stage);
+  roi_body(frames, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
+           __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm);
 }
 
 // ---- ROI selection: detections of the allowed classes -> dense list, image-major, order kept ----
@@ -353,7 +337,7 @@ __global__ void __launch_bounds__(1024) select_rois_kernel(const float* __restri
 
 }  // namespace
 
-static size_t roi_smem_bytes() { return ((sizeof(RoiSmem) + 15) & ~(size_t)15) + kStageBytes; }
+static size_t roi_smem_bytes() { return sizeof(RoiSmem); }
 
 extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t pitch,
                                         int64_t batch_stride, const float* boxes, const int* batch_idx,
@@ -362,14 +346,13 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
   B200_REQUIRE(frames && boxes && batch_idx && dst && valid, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && N >= 0 && pad >= 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
-  B200_REQUIRE(size > 0 && size <= kMaxSize, B200YOLO_ERR_UNSUPPORTED);
+  B200_REQUIRE(size == kS, B200YOLO_ERR_UNSUPPORTED);
   if (N == 0) return B200YOLO_OK;
   const size_t smem = roi_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
-  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
-                                                           batch_idx, roi_count, pad, size, dst, valid);
+  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, B, H, W, pitch, batch_stride, boxes, batch_idx,
+                                                           roi_count, pad, dst, valid);
   return b200_launch_status();
 }
 
@@ -382,15 +365,13 @@ extern "C" int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H,
                B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && max_det > 0 && nc > 0 && roi_cap > 0 && pad >= 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
-  B200_REQUIRE(size > 0 && size <= kMaxSize, B200YOLO_ERR_UNSUPPORTED);
+  B200_REQUIRE(size == kS, B200YOLO_ERR_UNSUPPORTED);
   const size_t smem = roi_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(roi_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
-  roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, det,
+  roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, B, H, W, pitch, batch_stride, det,
                                                                     det_count, roi_cnt, max_det, class_mask, nc, pad,
-                                                                    size, dst, roi_batch, roi_det, valid, roi_total,
-                                                                    roi_cap);
+                                                                    dst, roi_batch, roi_det, valid, roi_total, roi_cap);
   return b200_launch_status();
 }
 
