@@ -117,14 +117,32 @@ def config1(dev):
     return out
 
 
+def calibration(dev):
+    """What plain torch copy / fill kernels reach on this GPU for K1's traffic mix (147 MB read, 315 MB written)."""
+    out = {}
+    src = torch.empty(147_456_000, dtype=torch.uint8, device=dev)
+    dst = torch.empty(78_643_200, dtype=torch.float32, device=dev)
+    big_a = torch.empty(256 * 1024 * 1024, dtype=torch.float32, device=dev)
+    big_b = torch.empty_like(big_a)
+    r = timed(lambda: dst.fill_(0.5), iters=10)
+    out["fill_315MB"] = {**r, "GBps": dst.numel() * 4 / (r["us_median"] * 1e-6) / 1e9}
+    r = timed(lambda: big_b.copy_(big_a), iters=10)
+    out["copy_1GiB"] = {**r, "GBps": 2 * big_a.numel() * 4 / (r["us_median"] * 1e-6) / 1e9}
+    r = timed(lambda: src.sum(), iters=10)
+    out["read_reduce_147MB_u8"] = {**r, "GBps": src.numel() / (r["us_median"] * 1e-6) / 1e9}
+    r = timed(lambda: big_a.sum(), iters=10)
+    out["read_reduce_1GiB_f32"] = {**r, "GBps": big_a.numel() * 4 / (r["us_median"] * 1e-6) / 1e9}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_extra.json"))
     ap.add_argument("--b3", type=int, default=256)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
-    res = {"config3_nms_heavy": config3(dev, B=args.b3), "config4_roi_4096": config4(dev),
-           "config1_single_frame": config1(dev)}
+    res = {"calibration": calibration(dev), "config3_nms_heavy": config3(dev, B=args.b3),
+           "config4_roi_4096": config4(dev), "config1_single_frame": config1(dev)}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     print(json.dumps(res))

@@ -17,6 +17,8 @@
 // HBM-bound: algorithmic bytes per frame = (64+nc)*A*4 read + 28 B per survivor written.
 // Compiled with -fmad=false: every add/mul below rounds separately, as the torch CPU ops do.
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace {
@@ -197,6 +199,287 @@ __global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L,
   emit(is_cand, b, a, x1, y1, x2, y2, score, cls, cand, cand_anchor, cand_count, cap);
 }
 
+// =================================================================================================
+// TMA-staged variant (the fast path; the kernel above is the fallback for unaligned shapes).
+//
+// The head is channel-major with the anchor axis contiguous, so a [128 anchors x 16 channels] box is a
+// 2-D tile of the (A, channels, B) tensor: one cp.async.bulk.tensor instruction (SASS UTMALDG) per 8 KB
+// chunk, completion on an mbarrier, zero fill past A.  A persistent CTA (256 threads) walks tiles of 128
+// anchors; the class chunks of tile t+1 are in flight in the second buffer set while tile t is reduced
+// (thread = anchor x channel-half, conflict-free LDS columns).  Survivors are rare at conf 0.25, so the 64
+// DFL channels are read lazily: a handful of candidates fetch them straight from global memory; when a
+// tile is dense (eval regime, conf 0.001) its [128 x 64] box tile is pulled through TMA as well and
+// decoded from shared memory by all 256 threads (thread = anchor x side-pair).
+// =================================================================================================
+constexpr int kTA = 128;          // anchors per tile
+constexpr int kCC = 16;           // class channels per TMA chunk (8 KB)
+constexpr int kDenseMin = 16;     // candidates in a tile from which the box tile is TMA-staged
+
+struct Segs {
+  int n;                          // tensor maps in use (1 = concatenated head, else one per level)
+  int tiles[B200YOLO_MAX_LEVELS]; // tiles per image in each segment
+  int first[B200YOLO_MAX_LEVELS]; // first global anchor index of the segment
+  int count[B200YOLO_MAX_LEVELS]; // anchors in the segment
+  int tiles_per_image;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(b200::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(b200::smem_u32(bar))
+      : "memory");
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(256, 2) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
+                                                            const __grid_constant__ CUtensorMap map1,
+                                                            const __grid_constant__ CUtensorMap map2, const Segs S,
+                                                            const Levels L, int B, int nc, int cls0, float conf,
+                                                            const uint32_t* __restrict__ class_mask,
+                                                            float* __restrict__ cand, int* __restrict__ cand_anchor,
+                                                            int* __restrict__ cand_count, int cap) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  __shared__ __align__(8) uint64_t full[2], boxbar;
+  __shared__ Part part[kTA];
+  __shared__ float dist[4][kTA];
+  __shared__ unsigned char flag[kTA];
+  const int nchunk = (nc + kCC - 1) / kCC;
+  const int set_bytes = nchunk * kTA * kCC * 4;
+  float* cls_buf[2] = {reinterpret_cast<float*>(dsm), reinterpret_cast<float*>(dsm + set_bytes)};
+  float* box_buf = reinterpret_cast<float*>(dsm + 2 * set_bytes);     // [64][kTA] (RAW only)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int al = tid & (kTA - 1), half = tid >> 7;                    // anchor-in-tile, channel half / side pair
+  const int total_tiles = S.tiles_per_image * B;
+
+  if (tid == 0) {
+    b200::mbar_init(&full[0], 1);
+    b200::mbar_init(&full[1], 1);
+    b200::mbar_init(&boxbar, 1);
+    b200::mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto locate = [&](int t, int& b, int& seg, int& a0) {     // tile id -> image, segment, first local anchor
+    b = t / S.tiles_per_image;
+    int r = t - b * S.tiles_per_image;
+    seg = 0;
+    if (S.n > 1 && r >= S.tiles[0]) { r -= S.tiles[0]; seg = 1; if (S.n > 2 && r >= S.tiles[1]) { r -= S.tiles[1]; seg = 2; } }
+    a0 = r * kTA;
+  };
+  auto map_of = [&](int seg) -> const CUtensorMap* { return seg == 0 ? &map0 : (seg == 1 ? &map1 : &map2); };
+  auto issue = [&](int t, int set) {                         // thread 0: all class chunks of tile t -> buffer set
+    int b, seg, a0;
+    locate(t, b, seg, a0);
+    b200::mbar_expect_tx(&full[set], (uint32_t)set_bytes);
+    for (int k = 0; k < nchunk; ++k)
+      tma_load_3d(cls_buf[set] + k * kTA * kCC, map_of(seg), a0, cls0 + k * kCC, b, &full[set]);
+  };
+
+  int t = blockIdx.x;
+  if (tid == 0) {
+    if (t < total_tiles) issue(t, 0);
+    if (t + (int)gridDim.x < total_tiles) issue(t + gridDim.x, 1);
+  }
+  int it = 0, box_phase = 0;
+  for (; t < total_tiles; t += gridDim.x, ++it) {
+    const int set = it & 1;
+    int b, seg, a0;
+    locate(t, b, seg, a0);
+    const int seg_first = seg == 0 ? S.first[0] : (seg == 1 ? S.first[1] : S.first[2]);
+    const int seg_count = seg == 0 ? S.count[0] : (seg == 1 ? S.count[1] : S.count[2]);
+    const int a_loc = a0 + al;                       // anchor index inside the segment
+    const int a = seg_first + a_loc;                 // global anchor index
+    const bool live = a_loc < seg_count;
+
+    b200::mbar_wait(&full[set], (it >> 1) & 1);
+    // ---- class reduction: thread = (anchor, channel half); columns of the staged chunks ----
+    float m = -INFINITY, m2 = -INFINITY;
+    int j = 0;
+    {
+      const float* col = cls_buf[set] + al;
+      const int cbeg = half * ((nchunk * kCC) >> 1), cend = cbeg + ((nchunk * kCC) >> 1);
+      j = cbeg;
+#pragma unroll 4
+      for (int c = cbeg; c < cend; c += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = col[(c + u) * kTA];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c + u < nc && v[u] > m) { m2 = m; m = v[u]; j = c + u; }
+      }
+    }
+    if (half == 1) part[al] = Part{m, m2, j};
+    __syncthreads();                                  // (1) every thread is done reading cls_buf[set]
+    if (tid == 0 && t + 2 * (int)gridDim.x < total_tiles) issue(t + 2 * gridDim.x, set);
+    float score = 0.f;
+    int cls = 0;
+    bool is_cand = false;
+    if (half == 0) {
+      const Part o = part[al];
+      if (o.m > m) { m2 = fmaxf(m, o.m2); m = o.m; j = o.j; }
+      score = RAW ? b200::sigmoid_torch(m) : m;
+      is_cand = live && (score > conf);
+      cls = j;
+    }
+    // per-lane level parameters (RAW decode) and element pointer of this anchor's channel 0
+    int off = 0, lw = L.w[0];
+    long long cs = L.cstride[0], bs = L.bstride[0];
+    const float* base = L.ptr[0];
+    float st = L.stride[0];
+#pragma unroll
+    for (int l = 1; l < B200YOLO_MAX_LEVELS; ++l) {
+      if (l < L.n && a >= L.off[l]) {
+        off = L.off[l]; lw = L.w[l]; cs = L.cstride[l]; bs = L.bstride[l]; base = L.ptr[l]; st = L.stride[l];
+      }
+    }
+    const int i = live ? a - off : 0;
+    const float* p = base + (long long)b * bs + i;
+    if (half == 0) {
+      if (RAW && is_cand && m2 > -INFINITY && b200::sigmoid_torch(m2) == score) {
+        const float* pc = p + (long long)cls0 * cs;   // lowest class index whose sigmoid ties the maximum
+        for (int c = 0; c < j; ++c)
+          if (b200::sigmoid_torch(pc[(long long)c * cs]) == score) { cls = c; break; }
+      }
+      if (is_cand && !class_allowed(class_mask, cls)) is_cand = false;
+      flag[al] = is_cand;
+    }
+    const int ncand = __syncthreads_count(is_cand);   // (2) also publishes flag[]
+    if (ncand == 0) continue;
+
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (RAW) {
+      const bool dense = ncand >= kDenseMin;
+      if (dense) {
+        // box tile [128 anchors x 64 DFL channels] through TMA, decoded from shared memory
+        if (tid == 0) {
+          b200::mbar_expect_tx(&boxbar, kTA * 4 * kReg * 4);
+          for (int k = 0; k < 4 * kReg / kCC; ++k)
+            tma_load_3d(box_buf + k * kTA * kCC, map_of(seg), a0, k * kCC, b, &boxbar);
+        }
+        b200::mbar_wait(&boxbar, box_phase & 1);
+        ++box_phase;
+      }
+      if (flag[al]) {
+        for (int sd = half * 2; sd < half * 2 + 2; ++sd) {       // this thread's two box sides
+          float v[kReg];
+          if (dense) {
+#pragma unroll
+            for (int k = 0; k < kReg; ++k) v[k] = box_buf[(sd * kReg + k) * kTA + al];
+          } else {
+#pragma unroll
+            for (int k = 0; k < kReg; ++k) v[k] = p[(long long)(sd * kReg + k) * cs];
+          }
+          float mx = v[0];
+#pragma unroll
+          for (int k = 1; k < kReg; ++k) mx = fmaxf(mx, v[k]);
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < kReg; ++k) { v[k] = b200::expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
+          float acc = 0.f;   // torch's 1x1 conv with arange weights: sequential fma over the 16 bins
+#pragma unroll
+          for (int k = 0; k < kReg; ++k) acc = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), acc);
+          dist[sd][al] = acc;
+        }
+      }
+      __syncthreads();                                // (3) dist[] complete; box_buf free again
+      if (half == 0 && is_cand) {
+        const float d0 = dist[0][al], d1 = dist[1][al], d2 = dist[2][al], d3 = dist[3][al];
+        const float ax = (float)(i % lw) + 0.5f, ay = (float)(i / lw) + 0.5f;
+        const float bx1 = ax - d0, by1 = ay - d1, bx2 = ax + d2, by2 = ay + d3;
+        const float cx = ((bx1 + bx2) / 2.0f) * st, cy = ((by1 + by2) / 2.0f) * st;
+        const float bw = (bx2 - bx1) * st, bh = (by2 - by1) * st;
+        const float hw = bw / 2.0f, hh = bh / 2.0f;
+        x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+      }
+    } else if (half == 0 && is_cand) {
+      const float cx = p[0], cy = p[cs], bw = p[2 * cs], bh = p[3 * cs];
+      const float hw = bw / 2.0f, hh = bh / 2.0f;
+      x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+    }
+    if (half == 0) emit(is_cand, b, a, x1, y1, x2, y2, score, cls, cand, cand_anchor, cand_count, cap);
+    (void)lane;
+  }
+}
+
+// ---- host: tensor-map construction through the driver entry point (no libcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;          // resolved once; read-only afterwards
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// (anchors, channels, B) fp32 tensor -> map with a [kTA x kCC x 1] box.  Returns false if TMA cannot express it.
+static bool make_map(CUtensorMap* map, const float* ptr, long long anchors, long long channels, long long B,
+                     long long chan_stride, long long batch_stride) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (chan_stride * 4) % 16 || (batch_stride * 4) % 16) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)anchors, (cuuint64_t)channels, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)chan_stride * 4, (cuuint64_t)batch_stride * 4};
+  cuuint32_t box[3] = {kTA, kCC, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Try the TMA path; returns -1000 if the shape is not eligible (caller falls back to the plain kernel).
+template <bool RAW>
+static int launch_tma(const Levels& L, int B, int channels, int nc, int cls0, float conf, const uint32_t* class_mask,
+                      float* cand, int* cand_anchor, int* cand_count, int cap, cudaStream_t stream) {
+  const int A = L.off[B200YOLO_MAX_LEVELS];
+  const int nchunk = (nc + kCC - 1) / kCC;
+  if ((nchunk * kCC) % 8 != 0) return -1000;
+  const size_t smem = 2 * (size_t)nchunk * kTA * kCC * 4 + (RAW ? (size_t)kTA * 4 * kReg * 4 : 0) + 1024;
+  if (smem > 200 * 1024) return -1000;
+  CUtensorMap maps[3];
+  Segs S;
+  // one map if the levels are views of one concatenated tensor, else one per level
+  bool concat = true;
+  for (int l = 1; l < L.n; ++l)
+    concat = concat && L.ptr[l] == L.ptr[0] + L.off[l] && L.cstride[l] == L.cstride[0] && L.bstride[l] == L.bstride[0];
+  if (concat) {
+    if (!make_map(&maps[0], L.ptr[0], A, channels, B, L.cstride[0], L.bstride[0])) return -1000;
+    maps[1] = maps[0]; maps[2] = maps[0];
+    S.n = 1; S.tiles[0] = (A + kTA - 1) / kTA; S.first[0] = 0; S.count[0] = A;
+    S.tiles[1] = S.tiles[2] = 0; S.first[1] = S.first[2] = 0; S.count[1] = S.count[2] = 0;
+    S.tiles_per_image = S.tiles[0];
+  } else {
+    S.n = L.n; S.tiles_per_image = 0;
+    for (int l = 0; l < B200YOLO_MAX_LEVELS; ++l) {
+      if (l < L.n) {
+        const int cnt = L.off[l + 1] - L.off[l];
+        if (!make_map(&maps[l], L.ptr[l], cnt, channels, B, L.cstride[l], L.bstride[l])) return -1000;
+        S.tiles[l] = (cnt + kTA - 1) / kTA; S.first[l] = L.off[l]; S.count[l] = cnt;
+        S.tiles_per_image += S.tiles[l];
+      } else {
+        maps[l] = maps[0]; S.tiles[l] = 0; S.first[l] = 0; S.count[l] = 0;
+      }
+    }
+  }
+  auto kern = decode_tma_kernel<RAW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const long long total = (long long)S.tiles_per_image * B;
+  const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int grid = (int)(total < (long long)B200_NUM_SMS * ctas_per_sm ? total : B200_NUM_SMS * ctas_per_sm);
+  kern<<<grid, 256, smem, stream>>>(maps[0], maps[1], maps[2], S, L, B, nc, cls0, conf, class_mask, cand, cand_anchor,
+                                    cand_count, cap);
+  return b200_launch_status();
+}
+
 }  // namespace
 
 extern "C" int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
@@ -224,6 +507,11 @@ extern "C" int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels
   }
   B200_REQUIRE(off <= (1LL << 30), B200YOLO_ERR_UNSUPPORTED);
   for (int l = n_levels; l <= B200YOLO_MAX_LEVELS; ++l) L.off[l] = (int)off;
+  {
+    const int rc = launch_tma<true>(L, B, 4 * kReg + nc, nc, 4 * kReg, conf_thres, class_mask, cand, cand_anchor,
+                                    cand_count, cap, (cudaStream_t)stream);
+    if (rc != -1000) return rc;
+  }
   dim3 grid((unsigned)((off + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
   decode_filter_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, nullptr, 0, nc, conf_thres, class_mask,
                                                                            cand, cand_anchor, cand_count, cap);
@@ -245,6 +533,11 @@ extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, i
     L.off[l] = l == 0 ? 0 : A;
   }
   L.off[B200YOLO_MAX_LEVELS] = A;
+  {
+    const int rc = launch_tma<false>(L, B, channels, nc, 4, conf_thres, class_mask, cand, cand_anchor, cand_count, cap,
+                                     (cudaStream_t)stream);
+    if (rc != -1000) return rc;
+  }
   dim3 grid((unsigned)((A + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
   decode_filter_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, pred, channels, nc, conf_thres,
                                                                             class_mask, cand, cand_anchor, cand_count,

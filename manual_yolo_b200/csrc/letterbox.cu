@@ -70,43 +70,72 @@ __device__ __forceinline__ float lb_cast<float>(const float* lut, int v) { retur
 template <>
 __device__ __forceinline__ uint8_t lb_cast<uint8_t>(const float*, int v) { return (uint8_t)v; }
 
-template <typename OutT>
-__device__ __forceinline__ void store_px4(const LbParams& p, int b, int oy, int ox, const OutT (&v)[4][3], int n) {
-  if constexpr (sizeof(OutT) == 4) {
-    float* base = reinterpret_cast<float*>(p.dst) + ((int64_t)b * 3 * p.outH + oy) * p.outW + ox;
-    const int64_t plane = (int64_t)p.outH * p.outW;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float* q = base + (p.swap_rb ? 2 - c : c) * plane;
-      if (n == 4 && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
-        b200::stg_stream_f4(q, make_float4(v[0][c], v[1][c], v[2][c], v[3][c]));
-      } else {
-        for (int k = 0; k < n; ++k) q[k] = v[k][c];
-      }
-    }
-  } else {
-    uint8_t* q = reinterpret_cast<uint8_t*>(p.dst) + (((int64_t)b * p.outH + oy) * p.outW + ox) * 3;
-    if (n == 4 && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
-      uint32_t w0 = v[0][0] | (v[0][1] << 8) | (v[0][2] << 16) | (v[1][0] << 24);
-      uint32_t w1 = v[1][1] | (v[1][2] << 8) | (v[2][0] << 16) | (v[2][1] << 24);
-      uint32_t w2 = v[2][2] | (v[3][0] << 8) | (v[3][1] << 16) | (v[3][2] << 24);
-      uint32_t* qw = reinterpret_cast<uint32_t*>(q);
-      qw[0] = w0; qw[1] = w1; qw[2] = w2;
-    } else {
-      for (int k = 0; k < n; ++k)
-        for (int c = 0; c < 3; ++c) q[k * 3 + c] = v[k][c];
-    }
-  }
-}
-
 constexpr int kRows = 8;     // output rows per CTA
 constexpr int kStages = 2;
 
+struct RowInfo { int r0, r1, b0, b1; };   // b0 < 0 marks a padding row
+
+// Per-thread output cursor: three plane pointers (f32) or one interleaved pointer (u8), advanced per row.
 template <typename OutT>
-__global__ void __launch_bounds__(256, 5) letterbox_kernel(const LbParams p) {
+struct OutCursor;
+template <>
+struct OutCursor<float> {
+  float *q0, *q1, *q2;     // planes of source channels 0,1,2 (B,G,R): swapped to R,G,B order when swap_rb
+  int64_t row_stride;
+  bool vec;
+  __device__ __forceinline__ void init(const LbParams& p, int b, int oy, int ox, int n) {
+    float* base = reinterpret_cast<float*>(p.dst) + ((int64_t)b * 3 * p.outH + oy) * p.outW + ox;
+    const int64_t plane = (int64_t)p.outH * p.outW;
+    q0 = base + (p.swap_rb ? 2 : 0) * plane;
+    q1 = base + plane;
+    q2 = base + (p.swap_rb ? 0 : 2) * plane;
+    row_stride = p.outW;
+    vec = (n == 4) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((plane & 3) == 0) && ((p.outW & 3) == 0);
+  }
+  __device__ __forceinline__ void store(const float (&v)[4][3], int n) {
+    if (vec) {
+      b200::stg_stream_f4(q0, make_float4(v[0][0], v[1][0], v[2][0], v[3][0]));
+      b200::stg_stream_f4(q1, make_float4(v[0][1], v[1][1], v[2][1], v[3][1]));
+      b200::stg_stream_f4(q2, make_float4(v[0][2], v[1][2], v[2][2], v[3][2]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n) { q0[k] = v[k][0]; q1[k] = v[k][1]; q2[k] = v[k][2]; }
+    }
+    q0 += row_stride; q1 += row_stride; q2 += row_stride;
+  }
+};
+template <>
+struct OutCursor<uint8_t> {
+  uint8_t* q;
+  int64_t row_stride;
+  bool vec;
+  __device__ __forceinline__ void init(const LbParams& p, int b, int oy, int ox, int n) {
+    q = reinterpret_cast<uint8_t*>(p.dst) + (((int64_t)b * p.outH + oy) * p.outW + ox) * 3;
+    row_stride = (int64_t)p.outW * 3;
+    vec = (n == 4) && ((reinterpret_cast<uintptr_t>(q) & 3) == 0) && ((row_stride & 3) == 0);
+  }
+  __device__ __forceinline__ void store(const uint8_t (&v)[4][3], int n) {
+    if (vec) {
+      uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+      qw[0] = v[0][0] | (v[0][1] << 8) | (v[0][2] << 16) | (v[1][0] << 24);
+      qw[1] = v[1][1] | (v[1][2] << 8) | (v[2][0] << 16) | (v[2][1] << 24);
+      qw[2] = v[2][2] | (v[3][0] << 8) | (v[3][1] << 16) | (v[3][2] << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n) { q[k * 3 + 0] = v[k][0]; q[k * 3 + 1] = v[k][1]; q[k * 3 + 2] = v[k][2]; }
+    }
+    q += row_stride;
+  }
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar[kStages];
   __shared__ float lut[256];
+  __shared__ RowInfo rows[kRows];
   __shared__ int span[2];
   const int b = blockIdx.y, tid = threadIdx.x;
   const int oy0 = blockIdx.x * kRows;
@@ -114,14 +143,17 @@ __global__ void __launch_bounds__(256, 5) letterbox_kernel(const LbParams p) {
   const int ox_base = blockIdx.z * (int)blockDim.x * 4;          // this CTA's column chunk
   const int ox0 = ox_base + tid * 4;
   const bool have = ox0 < p.outW;
+  const int npx = have ? min(4, p.outW - ox0) : 0;
 
   for (int v = tid; v < 256; v += blockDim.x) lut[v] = b200::u8_div255(v);
-  if (tid == 0) {
-    if (p.bulk_ok) {
-      for (int s = 0; s < kStages; ++s) b200::mbar_init(&bar[s], 1);
-      b200::mbar_fence_init();
-    }
-    // byte span of a source row this chunk's columns reference (16-byte granular)
+  if (tid < nrows) {            // vertical taps of this CTA's rows (shared by every thread)
+    const int oy = oy0 + tid;
+    RowInfo ri{0, 0, -1, 0};
+    if (oy >= p.top && oy < p.top + p.new_h) cv_linear_tap_v(oy - p.top, p.scale_y, p.H, ri.r0, ri.r1, ri.b0, ri.b1);
+    rows[tid] = ri;
+  }
+  if (tid == 32 || (blockDim.x <= 32 && tid == 0)) {
+    // byte span of a source row this chunk's columns reference (16-byte granular for the bulk copy)
     const int lo_ox = max(ox_base, p.left);
     const int hi_ox = min(min(ox_base + (int)blockDim.x * 4, p.outW), p.left + p.new_w) - 1;
     int blo = 0, bhi = 0;
@@ -130,43 +162,40 @@ __global__ void __launch_bounds__(256, 5) letterbox_kernel(const LbParams p) {
       cv_linear_tap(lo_ox - p.left, p.scale_x, p.W, s_lo, t0, t1);
       cv_linear_tap(hi_ox - p.left, p.scale_x, p.W, s_hi, t0, t1);
       blo = (s_lo * 3) & ~15;
-      bhi = min(p.row_bytes, ((min(s_hi + 2, p.W) * 3) + 15) & ~15);
-      if (!p.bulk_ok) bhi = min(s_hi + 2, p.W) * 3;
+      bhi = p.bulk_ok ? min(p.row_bytes, ((min(s_hi + 2, p.W) * 3) + 15) & ~15) : min(s_hi + 2, p.W) * 3;
     }
     span[0] = blo; span[1] = bhi;
   }
+  if (tid == 0 && p.bulk_ok) {
+    for (int s = 0; s < kStages; ++s) b200::mbar_init(&bar[s], 1);
+    b200::mbar_fence_init();
+  }
   // horizontal taps of this thread's 4 pixels: derived once, kept in registers for all kRows rows
-  int sx[4], a0[4], a1[4];
-  bool in[4];
+  int off[4], a0[4], a1[4];
+  bool in[4], all_in = true, pass_h = true;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int ox = ox0 + k;
     in[k] = have && (ox >= p.left) && (ox < p.left + p.new_w);
-    sx[k] = 0; a0[k] = 2048; a1[k] = 0;
-    if (in[k]) cv_linear_tap(ox - p.left, p.scale_x, p.W, sx[k], a0[k], a1[k]);
+    off[k] = 0; a0[k] = 2048; a1[k] = 0;
+    if (in[k]) cv_linear_tap(ox - p.left, p.scale_x, p.W, off[k], a0[k], a1[k]);
+    all_in &= in[k];
+    pass_h &= (a0[k] == 2048) && (a1[k] == 0);
   }
-  __syncthreads();
+  const bool cta_pass_h = __syncthreads_and(pass_h);              // also publishes rows[], span[], lut[], barriers
   const int blo = span[0], nbytes = span[1] - span[0];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) sx[k] = sx[k] * 3 - blo;            // byte offset inside the staged span
+  for (int k = 0; k < 4; ++k) off[k] = in[k] ? off[k] * 3 - blo : 0;   // byte offset inside the staged span
 
   const uint8_t* frame = p.src + (int64_t)b * p.bstride + blo;
-  // vertical taps of output row oy (CTA-uniform)
-  auto row_taps = [&](int oy, int& r0, int& r1, int& b0, int& b1) -> bool {
-    const bool interior = (oy >= p.top) && (oy < p.top + p.new_h) && nbytes > 0;
-    r0 = r1 = 0; b0 = 2048; b1 = 0;
-    if (interior) cv_linear_tap_v(oy - p.top, p.scale_y, p.H, r0, r1, b0, b1);
-    return interior;
-  };
-  // stage the source rows of output row `oy` into ring slot `s`
-  auto prefetch = [&](int oy, int s) {
-    int r0, r1, b0, b1;
-    if (!row_taps(oy, r0, r1, b0, b1)) return;
-    const bool need1 = (b1 != 0) && (r1 != r0);
+  auto prefetch = [&](int r, int s) {        // stage the source rows of CTA row r into ring slot s
+    const RowInfo ri = rows[r];
+    if (ri.b0 < 0 || nbytes <= 0) return;
+    const bool need1 = (ri.b1 != 0) && (ri.r1 != ri.r0);
     uint8_t* d0 = smem + (size_t)s * 2 * p.row_smem;
     uint8_t* d1 = d0 + p.row_smem;
-    const uint8_t* g0 = frame + (int64_t)r0 * p.pitch;
-    const uint8_t* g1 = frame + (int64_t)r1 * p.pitch;
+    const uint8_t* g0 = frame + (int64_t)ri.r0 * p.pitch;
+    const uint8_t* g1 = frame + (int64_t)ri.r1 * p.pitch;
     if (p.bulk_ok) {
       if (tid == 0) {
         b200::mbar_expect_tx(&bar[s], need1 ? 2u * nbytes : (uint32_t)nbytes);
@@ -181,58 +210,68 @@ __global__ void __launch_bounds__(256, 5) letterbox_kernel(const LbParams p) {
     }
   };
 
-  prefetch(oy0, 0);
+  OutCursor<OutT> cur;
+  if (have) cur.init(p, b, oy0, ox0, npx);
   const OutT padv = lb_cast<OutT>(lut, p.pad_value);
-  int uses[kStages] = {0, 0};                        // completed phases per ring slot (only interior rows arm it)
+  int uses0 = 0, uses1 = 0;                  // completed phases per ring slot (only interior rows arm it)
+  prefetch(0, 0);
   for (int r = 0; r < nrows; ++r) {
-    const int oy = oy0 + r, s = r & 1;
-    int r0, r1, b0, b1;
-    const bool interior = row_taps(oy, r0, r1, b0, b1);
-    if (r + 1 < nrows) prefetch(oy + 1, s ^ 1);      // slot s^1 was released by the barrier ending row r-1
-    if (interior) {
-      if (p.bulk_ok) {
-        if (s == 0) { b200::mbar_wait(&bar[0], uses[0] & 1); ++uses[0]; }
-        else { b200::mbar_wait(&bar[1], uses[1] & 1); ++uses[1]; }
-      } else {
-        __syncthreads();
-      }
+    const int s = r & 1;
+    const RowInfo ri = rows[r];
+    if (r + 1 < nrows) prefetch(r + 1, s ^ 1);       // slot s^1 was released by the barrier ending row r-1
+    OutT v[4][3];
+    if (ri.b0 < 0 || nbytes <= 0) {                  // CTA-uniform: padding row / chunk fully in the side padding
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k][0] = v[k][1] = v[k][2] = padv;
+      if (have) cur.store(v, npx);
+      __syncthreads();
+      continue;
+    }
+    if (p.bulk_ok) {
+      if (s == 0) { b200::mbar_wait(&bar[0], uses0 & 1); ++uses0; }
+      else { b200::mbar_wait(&bar[1], uses1 & 1); ++uses1; }
+    } else {
+      __syncthreads();
     }
     const uint8_t* row0 = smem + (size_t)s * 2 * p.row_smem;
-    const uint8_t* row1 = ((b1 != 0) && (r1 != r0)) ? row0 + p.row_smem : row0;
-    const bool pass_v = (b1 == 0) && (b0 == 2048);
     if (have) {
-      OutT v[4][3];
+      if (cta_pass_h && ri.b1 == 0 && ri.b0 == 2048) {
+        // exact integer decimation (weights 2048/0 on both axes): the output IS a source pixel
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!(interior && in[k])) {
-          v[k][0] = v[k][1] = v[k][2] = padv;
-          continue;
-        }
-        uint32_t lo, hi;
-        load6(row0, sx[k], lo, hi);
-        if (pass_v && a1[k] == 0 && a0[k] == 2048) {       // exact integer decimation: the source pixel itself
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(row0 + (off[k] & ~3));
+          const uint32_t lo = __funnelshift_r(w[0], w[1], (off[k] & 3) * 8);
           v[k][0] = lb_cast<OutT>(lut, (int)(lo & 0xff));
           v[k][1] = lb_cast<OutT>(lut, (int)((lo >> 8) & 0xff));
           v[k][2] = lb_cast<OutT>(lut, (int)((lo >> 16) & 0xff));
-          continue;
         }
-        int S0[3], S1[3] = {0, 0, 0};
-        S0[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
-        S0[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
-        S0[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
-        if (b1 != 0) {
-          load6(row1, sx[k], lo, hi);
+      } else {
+        const uint8_t* row1 = ((ri.b1 != 0) && (ri.r1 != ri.r0)) ? row0 + p.row_smem : row0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t lo, hi;
+          load6(row0, off[k], lo, hi);
+          int S0[3], S1[3];
+          S0[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
+          S0[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
+          S0[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
+          load6(row1, off[k], lo, hi);
           S1[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];
           S1[1] = (int)((lo >> 8) & 0xff) * a0[k] + (int)(hi & 0xff) * a1[k];
           S1[2] = (int)((lo >> 16) & 0xff) * a0[k] + (int)((hi >> 8) & 0xff) * a1[k];
-        }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int q = (((b0 * (S0[c] >> 4)) >> 16) + ((b1 * (S1[c] >> 4)) >> 16) + 2) >> 2;
-          v[k][c] = lb_cast<OutT>(lut, q);
+          for (int c = 0; c < 3; ++c) {
+            const int q = (((ri.b0 * (S0[c] >> 4)) >> 16) + ((ri.b1 * (S1[c] >> 4)) >> 16) + 2) >> 2;
+            v[k][c] = lb_cast<OutT>(lut, q);
+          }
         }
       }
-      store_px4<OutT>(p, b, oy, ox0, v, min(4, p.outW - ox0));
+      if (!all_in) {                                  // side padding columns (edge threads only)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!in[k]) v[k][0] = v[k][1] = v[k][2] = padv;
+      }
+      cur.store(v, npx);
     }
     __syncthreads();   // every thread is done with ring slot s: it may be refilled for row r+2
   }

@@ -11,7 +11,7 @@
 // (SURVEY.md Appendix A.11 / B.4).  All size arithmetic (double division, banker's rounding of the
 // crop offset) is done on the device exactly as Python/C do it on the host.
 //
-// One CTA per ROI: 128 threads build the two coefficient tables (only the 64 output columns/rows
+// One CTA per ROI (384 threads = 3 channels x 64 columns x 2 row phases): 128 threads build the two coefficient tables (only the 64 output columns/rows
 // that survive the centre crop), the horizontal pass writes a uint8 strip into shared memory, the
 // vertical pass streams coalesced fp32 rows to the planar (3,size,size) output.
 // HBM-bound: algorithmic bytes per ROI = crop_h*crop_w*3 read + 3*size*size*4 written.
@@ -21,7 +21,9 @@
 namespace {
 
 constexpr int kS = 64;           // output side (the rank classifier's imgsz; class.py:26, args.yaml imgsz: 64)
-constexpr int kThreads = 3 * kS; // one thread per (channel, output column)
+constexpr int kRowPar = 2;       // row phases: threads sharing a (channel, column) interleave over rows
+constexpr int kCols = 3 * kS;    // (channel, output column) pairs
+constexpr int kThreads = kCols * kRowPar;
 constexpr int kMaxTaps = 64;     // ksize = ceil(support)*2+1 <= 64  <=> scale <= 31
 constexpr int kFastTaps = 8;     // taps kept in registers (scale <= 3.5: every rank-card crop)
 constexpr int kRowsMax = 128;    // uint8 strip rows staged per vertical tile (>= kMaxTaps)
@@ -85,7 +87,8 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
                          int bi, int bx1, int by1, int bx2, int by2, int pad, float* __restrict__ out,
                          int* __restrict__ valid_out, RoiSmem& sm) {
   const int tid = threadIdx.x;
-  const int c = tid / kS, xx = tid % kS;       // warp = 32 consecutive columns of one channel
+  const int rp = tid / kCols, tcol = tid % kCols;
+  const int c = tcol / kS, xx = tcol % kS;     // warp = 32 consecutive columns of one channel, one row phase
   // ---- safe_crop (detect.py:100-113) ----
   const int cx1 = max(0, min(W - 1, bx1 - pad)), cx2 = max(0, min(W, bx2 + pad));
   const int cy1 = max(0, min(H - 1, by1 - pad)), cy2 = max(0, min(H, by2 + pad));
@@ -142,9 +145,29 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
     while (t1 < kS && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kRowsMax) ++t1;
     const int rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
     // ---- horizontal pass: this thread's column for every referenced row ----
-    if (fast_x) {
+    if (xcnt <= 4) {
+      // <= 4 taps (every up-scale and down-scales to 1.5x): 4 rows x 4 taps of byte loads in flight
+      for (int rr = rp; rr < rows; rr += 4 * kRowPar) {
+        int px[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r2 = min(rr + u * kRowPar, rows - 1);
+          const uint8_t* p = col + (int64_t)(rmin + r2) * pitch;
+#pragma unroll
+          for (int x = 0; x < 4; ++x) px[u][x] = (x < xcnt) ? (int)__ldg(p + x * 3) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r2 = rr + u * kRowPar;
+          int acc = 1 << (kPrec - 1);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) acc += px[u][x] * kx[x];
+          if (r2 < rows) sm.strip[r2][c][xx] = (uint8_t)clip8(acc);
+        }
+      }
+    } else if (fast_x) {
 #pragma unroll 2
-      for (int rr = 0; rr < rows; ++rr) {
+      for (int rr = rp; rr < rows; rr += kRowPar) {
         const uint8_t* p = col + (int64_t)(rmin + rr) * pitch;
         int acc = 1 << (kPrec - 1);
 #pragma unroll
@@ -153,7 +176,7 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
         sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
       }
     } else {
-      for (int rr = 0; rr < rows; ++rr) {
+      for (int rr = rp; rr < rows; rr += kRowPar) {
         const uint8_t* p = col + (int64_t)(rmin + rr) * pitch;
         int acc = 1 << (kPrec - 1);
         for (int x = 0; x < xcnt; ++x) acc += (int)__ldg(p + x * 3) * kx_big[x];
@@ -162,7 +185,7 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
     }
     __syncthreads();
     // ---- vertical pass + BGR->RGB + /255: coalesced 128-byte rows per warp ----
-    for (int yy = t0; yy < t1; ++yy) {
+    for (int yy = t0 + rp; yy < t1; yy += kRowPar) {
       const int ymin = sm.yb[yy][0] - rmin, cnt = sm.yb[yy][1];
       int acc = 1 << (kPrec - 1);
       for (int y = 0; y < cnt; ++y) acc += (int)sm.strip[ymin + y][c][xx] * sm.yk[yy][y];
@@ -175,7 +198,7 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
 }
 
 // ROI list form: boxes (N,4) float + batch_idx (N).
-__global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
+__global__ void __launch_bounds__(kThreads, 3) roi_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
                                                        const float* __restrict__ boxes,
                                                        const int* __restrict__ batch_idx,
                                                        const int* __restrict__ roi_count, int pad,
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) roi_kernel(const uint8_t* __restrict
 
 // Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
 // the allow-list, from the per-image counts the NMS kernel wrote -- no separate selection launch.
-__global__ void __launch_bounds__(kThreads) roi_det_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
+__global__ void __launch_bounds__(kThreads, 3) roi_det_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
                                                            const float* __restrict__ det,
                                                            const int* __restrict__ det_count,
                                                            const int* __restrict__ roi_cnt, int max_det,
