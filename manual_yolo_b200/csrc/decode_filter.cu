@@ -17,8 +17,6 @@
 // HBM-bound: algorithmic bytes per frame = (64+nc)*A*4 read + 28 B per survivor written.
 // Compiled with -fmad=false: every add/mul below rounds separately, as the torch CPU ops do.
 
-#include <cuda.h>
-
 #include "common.cuh"
 
 namespace {
@@ -58,6 +56,24 @@ __device__ __forceinline__ void emit(bool is_cand, int b, int a, float x1, float
       row[0] = make_float2(x1, y1);
       row[1] = make_float2(x2, y2);
       row[2] = make_float2(score, (float)cls);
+      cand_anchor[(int64_t)b * cap + slot] = a;
+    }
+  }
+}
+
+// Survivor whose box is decoded later (raw-head fast path): slot, score, class, anchor only.
+__device__ __forceinline__ void emit_pending(bool is_cand, int b, int a, float score, int cls, float* cand,
+                                             int* cand_anchor, int* cand_count, int cap) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == (__ffs(ballot) - 1)) base = atomicAdd(&cand_count[b], __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+  if (is_cand) {
+    const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < cap) {
+      reinterpret_cast<float2*>(cand + ((int64_t)b * cap + slot) * 6)[2] = make_float2(score, (float)cls);
       cand_anchor[(int64_t)b * cap + slot] = a;
     }
   }
@@ -200,130 +216,146 @@ __global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L,
 }
 
 // =================================================================================================
-// TMA-staged variant (the fast path; the kernel above is the fallback for unaligned shapes).
-//
-// The head is channel-major with the anchor axis contiguous, so a [128 anchors x 16 channels] box is a
-// 2-D tile of the (A, channels, B) tensor: one cp.async.bulk.tensor instruction (SASS UTMALDG) per 8 KB
-// chunk, completion on an mbarrier, zero fill past A.  A persistent CTA (256 threads) walks tiles of 128
-// anchors; the class chunks of tile t+1 are in flight in the second buffer set while tile t is reduced
-// (thread = anchor x channel-half, conflict-free LDS columns).  Survivors are rare at conf 0.25, so the 64
-// DFL channels are read lazily: a handful of candidates fetch them straight from global memory; when a
-// tile is dense (eval regime, conf 0.001) its [128 x 64] box tile is pulled through TMA as well and
-// decoded from shared memory by all 256 threads (thread = anchor x side-pair).
+// Vectorised variant (the fast path; the kernel above is the fallback for shapes that are not
+// 16-byte aligned).  A CTA of 256 threads covers 256 consecutive anchors of one flat segment (the whole
+// concatenated head, or one level tensor): thread = (channel quarter q, anchor quad), i.e. every load is
+// a 128-bit LDG of 4 consecutive anchors of one class channel, 8 of them in flight per thread, with
+// CTA-uniform strides so the address arithmetic is one pointer bump per load.  The partial
+// (max, runner-up, argmax) triples go through shared memory (SoA, conflict-free) and thread t then owns
+// anchor t: merge in class order, sigmoid, threshold.  Lazy DFL: only surviving anchors read their 64
+// box channels (coalesced across the owners of a dense tile), softmax expectation per side, decode, emit.
 // =================================================================================================
-constexpr int kTA = 128;          // anchors per tile
-constexpr int kCC = 16;           // class channels per TMA chunk (8 KB)
-constexpr int kDenseMin = 16;     // candidates in a tile from which the box tile is TMA-staged
+constexpr int kVA = 256;          // anchors per CTA
 
-struct Segs {
-  int n;                          // tensor maps in use (1 = concatenated head, else one per level)
-  int tiles[B200YOLO_MAX_LEVELS]; // tiles per image in each segment
-  int first[B200YOLO_MAX_LEVELS]; // first global anchor index of the segment
-  int count[B200YOLO_MAX_LEVELS]; // anchors in the segment
-  int tiles_per_image;
+struct FlatSegs {
+  const float* ptr[B200YOLO_MAX_LEVELS];
+  long long bstride[B200YOLO_MAX_LEVELS], cstride[B200YOLO_MAX_LEVELS];
+  int count[B200YOLO_MAX_LEVELS], first[B200YOLO_MAX_LEVELS];
+  int n;
 };
 
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(b200::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2),
-      "r"(b200::smem_u32(bar))
-      : "memory");
-}
-
 template <bool RAW>
-__global__ void __launch_bounds__(256, 2) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
-                                                            const __grid_constant__ CUtensorMap map1,
-                                                            const __grid_constant__ CUtensorMap map2, const Segs S,
-                                                            const Levels L, int B, int nc, int cls0, float conf,
-                                                            const uint32_t* __restrict__ class_mask,
+__global__ void __launch_bounds__(256, 4) decode_vec_kernel(const FlatSegs S, const Levels L, int nc, int cls0,
+                                                            float conf, const uint32_t* __restrict__ class_mask,
                                                             float* __restrict__ cand, int* __restrict__ cand_anchor,
                                                             int* __restrict__ cand_count, int cap) {
-  extern __shared__ __align__(1024) uint8_t dsm[];
-  __shared__ __align__(8) uint64_t full[2], boxbar;
-  __shared__ Part part[kTA];
-  __shared__ float dist[4][kTA];
-  __shared__ unsigned char flag[kTA];
-  const int nchunk = (nc + kCC - 1) / kCC;
-  const int set_bytes = nchunk * kTA * kCC * 4;
-  float* cls_buf[2] = {reinterpret_cast<float*>(dsm), reinterpret_cast<float*>(dsm + set_bytes)};
-  float* box_buf = reinterpret_cast<float*>(dsm + 2 * set_bytes);     // [64][kTA] (RAW only)
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int al = tid & (kTA - 1), half = tid >> 7;                    // anchor-in-tile, channel half / side pair
-  const int total_tiles = S.tiles_per_image * B;
+  __shared__ __align__(16) float pm[kQ][kVA], pm2[kQ][kVA];
+  __shared__ __align__(16) int pj[kQ][kVA];
+  const int sg = blockIdx.z, b = blockIdx.y, tid = threadIdx.x;
+  // CTA-uniform segment parameters (static indexing only)
+  const float* sptr = S.ptr[0];
+  long long sbs = S.bstride[0], scs = S.cstride[0];
+  int scount = S.count[0], sfirst = S.first[0];
+#pragma unroll
+  for (int l = 1; l < B200YOLO_MAX_LEVELS; ++l)
+    if (sg == l) { sptr = S.ptr[l]; sbs = S.bstride[l]; scs = S.cstride[l]; scount = S.count[l]; sfirst = S.first[l]; }
+  const int a_cta = blockIdx.x * kVA;
+  if (a_cta >= scount) return;
 
-  if (tid == 0) {
-    b200::mbar_init(&full[0], 1);
-    b200::mbar_init(&full[1], 1);
-    b200::mbar_init(&boxbar, 1);
-    b200::mbar_fence_init();
+  // ---- phase 1: thread = (quarter q, 4 consecutive anchors); 128-bit loads, 8 in flight ----
+  {
+    const int q = tid >> 6, t4 = (tid & 63) * 4;
+    const bool live = a_cta + t4 < scount;                    // segment counts are multiples of 4
+    const int cq = (nc + kQ - 1) / kQ;
+    const int c0 = q * cq, c1 = min(nc, c0 + cq);
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float m2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int j[4] = {c0, c0, c0, c0};
+    if (live) {
+      const float* p = sptr + (long long)b * sbs + (long long)(cls0 + c0) * scs + a_cta + t4;
+      for (int c = c0; c < c1; c += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (c + u < c1) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                         : "l"(p + (long long)u * scs));
+          } else {
+            v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          }
+        }
+        p += 8 * scs;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (v[u].x > m[0]) { m2[0] = m[0]; m[0] = v[u].x; j[0] = c + u; }
+          if (v[u].y > m[1]) { m2[1] = m[1]; m[1] = v[u].y; j[1] = c + u; }
+          if (v[u].z > m[2]) { m2[2] = m[2]; m[2] = v[u].z; j[2] = c + u; }
+          if (v[u].w > m[3]) { m2[3] = m[3]; m[3] = v[u].w; j[3] = c + u; }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(&pm[q][t4]) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(&pm2[q][t4]) = make_float4(m2[0], m2[1], m2[2], m2[3]);
+    *reinterpret_cast<int4*>(&pj[q][t4]) = make_int4(j[0], j[1], j[2], j[3]);
   }
   __syncthreads();
 
-  auto locate = [&](int t, int& b, int& seg, int& a0) {     // tile id -> image, segment, first local anchor
-    b = t / S.tiles_per_image;
-    int r = t - b * S.tiles_per_image;
-    seg = 0;
-    if (S.n > 1 && r >= S.tiles[0]) { r -= S.tiles[0]; seg = 1; if (S.n > 2 && r >= S.tiles[1]) { r -= S.tiles[1]; seg = 2; } }
-    a0 = r * kTA;
-  };
-  auto map_of = [&](int seg) -> const CUtensorMap* { return seg == 0 ? &map0 : (seg == 1 ? &map1 : &map2); };
-  auto issue = [&](int t, int set) {                         // thread 0: all class chunks of tile t -> buffer set
-    int b, seg, a0;
-    locate(t, b, seg, a0);
-    b200::mbar_expect_tx(&full[set], (uint32_t)set_bytes);
-    for (int k = 0; k < nchunk; ++k)
-      tma_load_3d(cls_buf[set] + k * kTA * kCC, map_of(seg), a0, cls0 + k * kCC, b, &full[set]);
-  };
-
-  int t = blockIdx.x;
-  if (tid == 0) {
-    if (t < total_tiles) issue(t, 0);
-    if (t + (int)gridDim.x < total_tiles) issue(t + gridDim.x, 1);
+  // ---- phase 2: thread t owns anchor t: merge quarters in class order, threshold ----
+  const int a_loc = a_cta + tid;
+  const int a = sfirst + a_loc;                               // global anchor index
+  const bool live = a_loc < scount;
+  float m = pm[0][tid], m2 = pm2[0][tid];
+  int j = pj[0][tid];
+#pragma unroll
+  for (int k = 1; k < kQ; ++k) {
+    const float tm = pm[k][tid];
+    if (tm > m) { m2 = fmaxf(m, pm2[k][tid]); m = tm; j = pj[k][tid]; }
   }
-  int it = 0, box_phase = 0;
-  for (; t < total_tiles; t += gridDim.x, ++it) {
-    const int set = it & 1;
-    int b, seg, a0;
-    locate(t, b, seg, a0);
-    const int seg_first = seg == 0 ? S.first[0] : (seg == 1 ? S.first[1] : S.first[2]);
-    const int seg_count = seg == 0 ? S.count[0] : (seg == 1 ? S.count[1] : S.count[2]);
-    const int a_loc = a0 + al;                       // anchor index inside the segment
-    const int a = seg_first + a_loc;                 // global anchor index
-    const bool live = a_loc < seg_count;
+  const float score = RAW ? b200::sigmoid_torch(m) : m;
+  bool is_cand = live && (score > conf);
+  if (!__syncthreads_or(is_cand)) return;                     // no survivor among these 256 anchors
 
-    b200::mbar_wait(&full[set], (it >> 1) & 1);
-    // ---- class reduction: thread = (anchor, channel half); columns of the staged chunks ----
-    float m = -INFINITY, m2 = -INFINITY;
-    int j = 0;
-    {
-      const float* col = cls_buf[set] + al;
-      const int cbeg = half * ((nchunk * kCC) >> 1), cend = cbeg + ((nchunk * kCC) >> 1);
-      j = cbeg;
-#pragma unroll 4
-      for (int c = cbeg; c < cend; c += 4) {
-        float v[4];
+  // per-lane level parameters (decode geometry) and this anchor's channel-0 element
+  int off = 0, lw = L.w[0];
+  long long cs = L.cstride[0], bs = L.bstride[0];
+  const float* base = L.ptr[0];
+  float st = L.stride[0];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = col[(c + u) * kTA];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (c + u < nc && v[u] > m) { m2 = m; m = v[u]; j = c + u; }
-      }
+  for (int l = 1; l < B200YOLO_MAX_LEVELS; ++l) {
+    if (l < L.n && a >= L.off[l]) {
+      off = L.off[l]; lw = L.w[l]; cs = L.cstride[l]; bs = L.bstride[l]; base = L.ptr[l]; st = L.stride[l];
     }
-    if (half == 1) part[al] = Part{m, m2, j};
-    __syncthreads();                                  // (1) every thread is done reading cls_buf[set]
-    if (tid == 0 && t + 2 * (int)gridDim.x < total_tiles) issue(t + 2 * gridDim.x, set);
-    float score = 0.f;
-    int cls = 0;
-    bool is_cand = false;
-    if (half == 0) {
-      const Part o = part[al];
-      if (o.m > m) { m2 = fmaxf(m, o.m2); m = o.m; j = o.j; }
-      score = RAW ? b200::sigmoid_torch(m) : m;
-      is_cand = live && (score > conf);
-      cls = j;
+  }
+  const int i = live ? a - off : 0;
+  const float* p = base + (long long)b * bs + i;
+  int cls = j;
+  if (RAW && is_cand && m2 > -INFINITY && b200::sigmoid_torch(m2) == score) {
+    const float* pc = p + (long long)cls0 * cs;               // lowest class index whose sigmoid ties the maximum
+    for (int c = 0; c < j; ++c)
+      if (b200::sigmoid_torch(pc[(long long)c * cs]) == score) { cls = c; break; }
+  }
+  if (is_cand && !class_allowed(class_mask, cls)) is_cand = false;
+
+  if (RAW) {
+    // boxes are decoded by box_decode_kernel from the compacted list: the streaming CTAs never wait on
+    // the (rare, latency-bound) DFL reads
+    emit_pending(is_cand, b, a, score, cls, cand, cand_anchor, cand_count, cap);
+  } else {
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (is_cand) {
+      const float cx = p[0], cy = p[cs], bw = p[2 * cs], bh = p[3 * cs];
+      const float hw = bw / 2.0f, hh = bh / 2.0f;
+      x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
     }
-    // per-lane level parameters (RAW decode) and element pointer of this anchor's channel 0
+    emit(is_cand, b, a, x1, y1, x2, y2, score, cls, cand, cand_anchor, cand_count, cap);
+  }
+}
+
+// Second half of the raw-head path: DFL decode of the compacted survivors.  Four lanes per candidate
+// (lane = box side): 16 bins each in one load round, softmax expectation exactly as torch computes it,
+// quad shuffle, then dist2bbox(xywh) * stride and xywh2xyxy in the reference's op order.
+__global__ void __launch_bounds__(256) box_decode_kernel(const Levels L, float* __restrict__ cand,
+                                                         const int* __restrict__ cand_anchor,
+                                                         const int* __restrict__ cand_count, int cap) {
+  const int b = blockIdx.y;
+  const int n = min(cand_count[b], cap);
+  const int lane = threadIdx.x & 31, sd = threadIdx.x & 3;
+  // grid-stride over blocks of 64 survivors: few CTAs per image, none launched just to exit
+  for (int blk = blockIdx.x; blk * 64 < n; blk += gridDim.x) {
+    const int slot = blk * 64 + (threadIdx.x >> 2);
+    const bool act = slot < n;
+    const int a = act ? cand_anchor[(int64_t)b * cap + slot] : 0;
     int off = 0, lw = L.w[0];
     long long cs = L.cstride[0], bs = L.bstride[0];
     const float* base = L.ptr[0];
@@ -334,149 +366,72 @@ __global__ void __launch_bounds__(256, 2) decode_tma_kernel(const __grid_constan
         off = L.off[l]; lw = L.w[l]; cs = L.cstride[l]; bs = L.bstride[l]; base = L.ptr[l]; st = L.stride[l];
       }
     }
-    const int i = live ? a - off : 0;
-    const float* p = base + (long long)b * bs + i;
-    if (half == 0) {
-      if (RAW && is_cand && m2 > -INFINITY && b200::sigmoid_torch(m2) == score) {
-        const float* pc = p + (long long)cls0 * cs;   // lowest class index whose sigmoid ties the maximum
-        for (int c = 0; c < j; ++c)
-          if (b200::sigmoid_torch(pc[(long long)c * cs]) == score) { cls = c; break; }
-      }
-      if (is_cand && !class_allowed(class_mask, cls)) is_cand = false;
-      flag[al] = is_cand;
+    const int i = a - off;
+    const float* p = base + (long long)b * bs + i + (long long)(sd * kReg) * cs;
+    float d = 0.f;
+    if (act) {
+      float v[kReg];
+#pragma unroll
+      for (int k = 0; k < kReg; ++k) v[k] = p[(long long)k * cs];
+      float mx = v[0];
+#pragma unroll
+      for (int k = 1; k < kReg; ++k) mx = fmaxf(mx, v[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kReg; ++k) { v[k] = b200::expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
+#pragma unroll
+      for (int k = 0; k < kReg; ++k) d = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), d);   // torch's conv: sequential fma
     }
-    const int ncand = __syncthreads_count(is_cand);   // (2) also publishes flag[]
-    if (ncand == 0) continue;
-
-    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-    if (RAW) {
-      const bool dense = ncand >= kDenseMin;
-      if (dense) {
-        // box tile [128 anchors x 64 DFL channels] through TMA, decoded from shared memory
-        if (tid == 0) {
-          b200::mbar_expect_tx(&boxbar, kTA * 4 * kReg * 4);
-          for (int k = 0; k < 4 * kReg / kCC; ++k)
-            tma_load_3d(box_buf + k * kTA * kCC, map_of(seg), a0, k * kCC, b, &boxbar);
-        }
-        b200::mbar_wait(&boxbar, box_phase & 1);
-        ++box_phase;
-      }
-      if (flag[al]) {
-        for (int sd = half * 2; sd < half * 2 + 2; ++sd) {       // this thread's two box sides
-          float v[kReg];
-          if (dense) {
-#pragma unroll
-            for (int k = 0; k < kReg; ++k) v[k] = box_buf[(sd * kReg + k) * kTA + al];
-          } else {
-#pragma unroll
-            for (int k = 0; k < kReg; ++k) v[k] = p[(long long)(sd * kReg + k) * cs];
-          }
-          float mx = v[0];
-#pragma unroll
-          for (int k = 1; k < kReg; ++k) mx = fmaxf(mx, v[k]);
-          float sum = 0.f;
-#pragma unroll
-          for (int k = 0; k < kReg; ++k) { v[k] = b200::expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
-          float acc = 0.f;   // torch's 1x1 conv with arange weights: sequential fma over the 16 bins
-#pragma unroll
-          for (int k = 0; k < kReg; ++k) acc = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), acc);
-          dist[sd][al] = acc;
-        }
-      }
-      __syncthreads();                                // (3) dist[] complete; box_buf free again
-      if (half == 0 && is_cand) {
-        const float d0 = dist[0][al], d1 = dist[1][al], d2 = dist[2][al], d3 = dist[3][al];
-        const float ax = (float)(i % lw) + 0.5f, ay = (float)(i / lw) + 0.5f;
-        const float bx1 = ax - d0, by1 = ay - d1, bx2 = ax + d2, by2 = ay + d3;
-        const float cx = ((bx1 + bx2) / 2.0f) * st, cy = ((by1 + by2) / 2.0f) * st;
-        const float bw = (bx2 - bx1) * st, bh = (by2 - by1) * st;
-        const float hw = bw / 2.0f, hh = bh / 2.0f;
-        x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
-      }
-    } else if (half == 0 && is_cand) {
-      const float cx = p[0], cy = p[cs], bw = p[2 * cs], bh = p[3 * cs];
+    const int q0 = lane & ~3;
+    const float d0 = __shfl_sync(0xffffffffu, d, q0), d1 = __shfl_sync(0xffffffffu, d, q0 + 1);
+    const float d2 = __shfl_sync(0xffffffffu, d, q0 + 2), d3 = __shfl_sync(0xffffffffu, d, q0 + 3);
+    if (act && sd == 0) {
+      const float ax = (float)(i % lw) + 0.5f, ay = (float)(i / lw) + 0.5f;
+      const float bx1 = ax - d0, by1 = ay - d1, bx2 = ax + d2, by2 = ay + d3;
+      const float cx = ((bx1 + bx2) / 2.0f) * st, cy = ((by1 + by2) / 2.0f) * st;
+      const float bw = (bx2 - bx1) * st, bh = (by2 - by1) * st;
       const float hw = bw / 2.0f, hh = bh / 2.0f;
-      x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+      float2* row = reinterpret_cast<float2*>(cand + ((int64_t)b * cap + slot) * 6);
+      row[0] = make_float2(cx - hw, cy - hh);
+      row[1] = make_float2(cx + hw, cy + hh);
     }
-    if (half == 0) emit(is_cand, b, a, x1, y1, x2, y2, score, cls, cand, cand_anchor, cand_count, cap);
-    (void)lane;
   }
 }
 
-// ---- host: tensor-map construction through the driver entry point (no libcuda link dependency) ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;          // resolved once; read-only afterwards
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// (anchors, channels, B) fp32 tensor -> map with a [kTA x kCC x 1] box.  Returns false if TMA cannot express it.
-static bool make_map(CUtensorMap* map, const float* ptr, long long anchors, long long channels, long long B,
-                     long long chan_stride, long long batch_stride) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn) return false;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (chan_stride * 4) % 16 || (batch_stride * 4) % 16) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)anchors, (cuuint64_t)channels, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)chan_stride * 4, (cuuint64_t)batch_stride * 4};
-  cuuint32_t box[3] = {kTA, kCC, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// Try the TMA path; returns -1000 if the shape is not eligible (caller falls back to the plain kernel).
+// Try the vectorised path; returns -1000 if the shape is not eligible (caller falls back to the scalar kernel).
 template <bool RAW>
-static int launch_tma(const Levels& L, int B, int channels, int nc, int cls0, float conf, const uint32_t* class_mask,
-                      float* cand, int* cand_anchor, int* cand_count, int cap, cudaStream_t stream) {
+static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, const uint32_t* class_mask, float* cand,
+                      int* cand_anchor, int* cand_count, int cap, cudaStream_t stream) {
   const int A = L.off[B200YOLO_MAX_LEVELS];
-  const int nchunk = (nc + kCC - 1) / kCC;
-  if ((nchunk * kCC) % 8 != 0) return -1000;
-  const size_t smem = 2 * (size_t)nchunk * kTA * kCC * 4 + (RAW ? (size_t)kTA * 4 * kReg * 4 : 0) + 1024;
-  if (smem > 200 * 1024) return -1000;
-  CUtensorMap maps[3];
-  Segs S;
-  // one map if the levels are views of one concatenated tensor, else one per level
+  FlatSegs S;
+  // one flat segment if the levels are views of one concatenated tensor, else one per level
   bool concat = true;
   for (int l = 1; l < L.n; ++l)
     concat = concat && L.ptr[l] == L.ptr[0] + L.off[l] && L.cstride[l] == L.cstride[0] && L.bstride[l] == L.bstride[0];
-  if (concat) {
-    if (!make_map(&maps[0], L.ptr[0], A, channels, B, L.cstride[0], L.bstride[0])) return -1000;
-    maps[1] = maps[0]; maps[2] = maps[0];
-    S.n = 1; S.tiles[0] = (A + kTA - 1) / kTA; S.first[0] = 0; S.count[0] = A;
-    S.tiles[1] = S.tiles[2] = 0; S.first[1] = S.first[2] = 0; S.count[1] = S.count[2] = 0;
-    S.tiles_per_image = S.tiles[0];
-  } else {
-    S.n = L.n; S.tiles_per_image = 0;
-    for (int l = 0; l < B200YOLO_MAX_LEVELS; ++l) {
-      if (l < L.n) {
-        const int cnt = L.off[l + 1] - L.off[l];
-        if (!make_map(&maps[l], L.ptr[l], cnt, channels, B, L.cstride[l], L.bstride[l])) return -1000;
-        S.tiles[l] = (cnt + kTA - 1) / kTA; S.first[l] = L.off[l]; S.count[l] = cnt;
-        S.tiles_per_image += S.tiles[l];
-      } else {
-        maps[l] = maps[0]; S.tiles[l] = 0; S.first[l] = 0; S.count[l] = 0;
-      }
+  S.n = concat ? 1 : L.n;
+  int maxcount = 0;
+  for (int l = 0; l < B200YOLO_MAX_LEVELS; ++l) {
+    const bool used = l < S.n;
+    S.ptr[l] = used ? L.ptr[l] : L.ptr[0];
+    S.bstride[l] = used ? L.bstride[l] : 0;
+    S.cstride[l] = used ? L.cstride[l] : 0;
+    S.count[l] = used ? (concat ? A : L.off[l + 1] - L.off[l]) : 0;
+    S.first[l] = used ? (concat ? 0 : L.off[l]) : 0;
+    if (used) {
+      if ((reinterpret_cast<uintptr_t>(S.ptr[l]) & 15) || (S.bstride[l] & 3) || (S.cstride[l] & 3) || (S.count[l] & 3))
+        return -1000;
+      if (S.count[l] > maxcount) maxcount = S.count[l];
     }
   }
-  auto kern = decode_tma_kernel<RAW>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const long long total = (long long)S.tiles_per_image * B;
-  const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
-  const int grid = (int)(total < (long long)B200_NUM_SMS * ctas_per_sm ? total : B200_NUM_SMS * ctas_per_sm);
-  kern<<<grid, 256, smem, stream>>>(maps[0], maps[1], maps[2], S, L, B, nc, cls0, conf, class_mask, cand, cand_anchor,
-                                    cand_count, cap);
+  dim3 grid((unsigned)((maxcount + kVA - 1) / kVA), B, S.n);
+  decode_vec_kernel<RAW><<<grid, 256, 0, stream>>>(S, L, nc, cls0, conf, class_mask, cand, cand_anchor, cand_count, cap);
+  if (RAW) {
+    const int amax = cap < A ? cap : A;               // an image has at most min(cap, A) stored survivors
+    const int per_image = (amax + 63) / 64;           // blocks of 64 survivors; CTAs grid-stride over them
+    const int want = (4 * B200_NUM_SMS + B - 1) / B;  // enough CTAs to fill the GPU when every anchor survives
+    dim3 grid2((unsigned)(per_image < want ? per_image : (want < 2 ? 2 : want)), B);
+    box_decode_kernel<<<grid2, 256, 0, stream>>>(L, cand, cand_anchor, cand_count, cap);
+  }
   return b200_launch_status();
 }
 
@@ -508,8 +463,8 @@ extern "C" int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels
   B200_REQUIRE(off <= (1LL << 30), B200YOLO_ERR_UNSUPPORTED);
   for (int l = n_levels; l <= B200YOLO_MAX_LEVELS; ++l) L.off[l] = (int)off;
   {
-    const int rc = launch_tma<true>(L, B, 4 * kReg + nc, nc, 4 * kReg, conf_thres, class_mask, cand, cand_anchor,
-                                    cand_count, cap, (cudaStream_t)stream);
+    const int rc = launch_vec<true>(L, B, nc, 4 * kReg, conf_thres, class_mask, cand, cand_anchor, cand_count, cap,
+                                    (cudaStream_t)stream);
     if (rc != -1000) return rc;
   }
   dim3 grid((unsigned)((off + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
@@ -534,7 +489,7 @@ extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, i
   }
   L.off[B200YOLO_MAX_LEVELS] = A;
   {
-    const int rc = launch_tma<false>(L, B, channels, nc, 4, conf_thres, class_mask, cand, cand_anchor, cand_count, cap,
+    const int rc = launch_vec<false>(L, B, nc, 4, conf_thres, class_mask, cand, cand_anchor, cand_count, cap,
                                      (cudaStream_t)stream);
     if (rc != -1000) return rc;
   }

@@ -28,6 +28,7 @@ constexpr int kMaxTaps = 64;     // ksize = ceil(support)*2+1 <= 64  <=> scale <
 constexpr int kFastTaps = 8;     // taps kept in registers (scale <= 3.5: every rank-card crop)
 constexpr int kRowsMax = 128;    // uint8 strip rows staged per vertical tile (>= kMaxTaps)
 constexpr int kPrec = 22;        // Pillow PRECISION_BITS = 32 - 8 - 2
+constexpr int kStageBytes = 48 * 1024;  // staged crop rows (a 115x105 rank crop needs ~37 KB)
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for output index `o` (triangle filter):
 // returns xmin, writes `cnt` fixed-point weights.
@@ -79,11 +80,23 @@ struct RoiSmem {
   int yk[kS][kMaxTaps];          // vertical weights (broadcast reads)
   uint8_t strip[kRowsMax][3][kS];  // horizontal-pass output, uint8 like Pillow's intermediate image
   int sel[4];
+  __align__(16) uint8_t stage[kStageBytes];   // referenced crop rows, staged once with coalesced loads
 };
+
+// Word load that never touches bytes outside [lo, hi) (the caller's frame buffer).
+__device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* a, const uint8_t* lo, const uint8_t* hi) {
+  if (a >= lo && a + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(a));
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (a + k >= lo && a + k < hi) w |= (uint32_t)__ldg(a + k) << (8 * k);
+  return w;
+}
 
 // One ROI per CTA, one thread per (channel c, output column xx).  (bi, x1..y2): already int()-truncated
 // box in source pixels.
-__device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
+__device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B, int H, int W, int64_t pitch,
+                         int64_t bstride,
                          int bi, int bx1, int by1, int bx2, int by2, int pad, float* __restrict__ out,
                          int* __restrict__ valid_out, RoiSmem& sm) {
   const int tid = threadIdx.x;
@@ -137,6 +150,11 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
 
   const uint8_t* crop = frames + (int64_t)bi * bstride + (int64_t)cy1 * pitch + (int64_t)cx1 * 3;
   const uint8_t* col = crop + (int64_t)xmin * 3 + c;
+  // horizontal span of source columns the 64 surviving output columns reference
+  const int x_lo = sm.xb[0][0];
+  const int span_bytes = (sm.xb[kS - 1][0] + sm.xb[kS - 1][1] - x_lo) * 3;
+  const int row_words = (span_bytes + 3 + 3) / 4;            // any 4-byte phase fits
+  const int row_stride = row_words * 4;
   int t0 = 0;
   while (t0 < kS) {
     // vertical tile [t0, t1): input rows [rmin, rmax) must fit the strip
@@ -144,8 +162,37 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
     int t1 = t0 + 1;
     while (t1 < kS && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kRowsMax) ++t1;
     const int rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
-    // ---- horizontal pass: this thread's column for every referenced row ----
-    if (xcnt <= 4) {
+    const bool staged = rows * row_stride <= kStageBytes;      // CTA-uniform
+    if (staged) {
+      // ---- stage the referenced crop rows: coalesced 32-bit loads, all in flight at once ----
+      for (int e = tid; e < rows * row_words; e += kThreads) {
+        const int rr = e / row_words, wd = e - rr * row_words;
+        const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+        const uint8_t* ga = g - (reinterpret_cast<uintptr_t>(g) & 3) + wd * 4;
+        reinterpret_cast<uint32_t*>(sm.stage + rr * row_stride)[wd] = load_word_guarded(ga, frames, buf_hi);
+      }
+      __syncthreads();
+      const int cofs = (xmin - x_lo) * 3 + c;
+      if (fast_x) {
+        for (int rr = rp; rr < rows; rr += kRowPar) {
+          const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+          const uint8_t* p = sm.stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + cofs;
+          int acc = 1 << (kPrec - 1);
+#pragma unroll
+          for (int x = 0; x < kFastTaps; ++x)
+            if (x < xcnt) acc += (int)p[x * 3] * kx[x];
+          sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
+        }
+      } else {
+        for (int rr = rp; rr < rows; rr += kRowPar) {
+          const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+          const uint8_t* p = sm.stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + cofs;
+          int acc = 1 << (kPrec - 1);
+          for (int x = 0; x < xcnt; ++x) acc += (int)p[x * 3] * kx_big[x];
+          sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
+        }
+      }
+    } else if (xcnt <= 4) {
       // <= 4 taps (every up-scale and down-scales to 1.5x): 4 rows x 4 taps of byte loads in flight
       for (int rr = rp; rr < rows; rr += 4 * kRowPar) {
         int px[4][4];
@@ -184,12 +231,29 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
       }
     }
     __syncthreads();
-    // ---- vertical pass + BGR->RGB + /255: coalesced 128-byte rows per warp ----
-    for (int yy = t0 + rp; yy < t1; yy += kRowPar) {
-      const int ymin = sm.yb[yy][0] - rmin, cnt = sm.yb[yy][1];
-      int acc = 1 << (kPrec - 1);
-      for (int y = 0; y < cnt; ++y) acc += (int)sm.strip[ymin + y][c][xx] * sm.yk[yy][y];
-      out[((2 - c) * kS + yy) * kS + xx] = b200::u8_div255(clip8(acc));
+    // ---- vertical pass + BGR->RGB + /255: thread = (channel, 4 adjacent columns), 8 row phases; one
+    //      32-bit LDS feeds 4 accumulators per tap, one 128-bit store per 4 outputs ----
+    {
+      const int vq = tid % 48, vph = tid / 48;           // 48 column quads (3 channels x 16), 8 row phases
+      const int vc = vq >> 4, vx = (vq & 15) * 4;
+      for (int yy = t0 + vph; yy < t1; yy += kThreads / 48) {
+        const int ymin = sm.yb[yy][0] - rmin, cnt = sm.yb[yy][1];
+        int a0 = 1 << (kPrec - 1), a1 = a0, a2 = a0, a3 = a0;
+        const uint8_t* sp = &sm.strip[ymin][vc][vx];
+        const int* kp = sm.yk[yy];
+#pragma unroll 4
+        for (int y = 0; y < cnt; ++y) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(sp + y * (3 * kS));
+          const int k = kp[y];
+          a0 += (int)(w & 0xff) * k;
+          a1 += (int)((w >> 8) & 0xff) * k;
+          a2 += (int)((w >> 16) & 0xff) * k;
+          a3 += (int)(w >> 24) * k;
+        }
+        float4 o = make_float4(b200::u8_div255(clip8(a0)), b200::u8_div255(clip8(a1)), b200::u8_div255(clip8(a2)),
+                               b200::u8_div255(clip8(a3)));
+        *reinterpret_cast<float4*>(out + ((2 - vc) * kS + yy) * kS + vx) = o;
+      }
     }
     __syncthreads();
     t0 = t1;
@@ -198,7 +262,8 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, int B, int H, int W
 }
 
 // ROI list form: boxes (N,4) float + batch_idx (N).
-__global__ void __launch_bounds__(kThreads, 3) roi_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
+__global__ void __launch_bounds__(kThreads, 2) roi_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B,
+                                                          int H, int W, int64_t pitch, int64_t bstride,
                                                        const float* __restrict__ boxes,
                                                        const int* __restrict__ batch_idx,
                                                        const int* __restrict__ roi_count, int pad,
@@ -208,14 +273,15 @@ __global__ void __launch_bounds__(kThreads, 3) roi_kernel(const uint8_t* __restr
   const int r = blockIdx.x;
   if (roi_count != nullptr && r >= *roi_count) return;
   // int() truncation of the float box (detect.py:581)
-  roi_body(frames, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
+  roi_body(frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
            __float2int_rz(boxes[r * 4 + 1]), __float2int_rz(boxes[r * 4 + 2]), __float2int_rz(boxes[r * 4 + 3]), pad,
            dst + (int64_t)r * 3 * kS * kS, valid + r, sm);
 }
 
 // Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
 // the allow-list, from the per-image counts the NMS kernel wrote -- no separate selection launch.
-__global__ void __launch_bounds__(kThreads, 3) roi_det_kernel(const uint8_t* __restrict__ frames, int B, int H, int W, int64_t pitch, int64_t bstride,
+__global__ void __launch_bounds__(kThreads, 2) roi_det_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi,
+                                                              int B, int H, int W, int64_t pitch, int64_t bstride,
                                                            const float* __restrict__ det,
                                                            const int* __restrict__ det_count,
                                                            const int* __restrict__ roi_cnt, int max_det,
@@ -277,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 3) roi_det_kernel(const uint8_t* __r
   const int i = sm.sel[2];
   const float* row = det + ((int64_t)b * max_det + i) * 6;
   if (tid == 0) { roi_batch[g] = b; roi_det[g] = i; }
-  roi_body(frames, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
+  roi_body(frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
            __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm);
 }
 
@@ -374,8 +440,9 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
   const size_t smem = roi_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, B, H, W, pitch, batch_stride, boxes, batch_idx,
-                                                           roi_count, pad, dst, valid);
+  const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
+  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
+                                                           batch_idx, roi_count, pad, dst, valid);
   return b200_launch_status();
 }
 
@@ -392,7 +459,8 @@ extern "C" int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H,
   const size_t smem = roi_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(roi_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, B, H, W, pitch, batch_stride, det,
+  const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
+  roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, det,
                                                                     det_count, roi_cnt, max_det, class_mask, nc, pad,
                                                                     dst, roi_batch, roi_det, valid, roi_total, roi_cap);
   return b200_launch_status();

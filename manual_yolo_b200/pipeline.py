@@ -6,7 +6,7 @@ This is the batched, device-resident form of the reference's per-frame loop
 preprocessing (``detect.py:121``).  The backbone/neck stay torch modules outside this package: the
 Detect-head tensor is an input here (``head``), the letterboxed network input an output (``net_in``).
 
-All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 5 launches of
+All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 6 launches of
 this package's kernels plus one counter memset, capturable into one CUDA graph.
 """
 
@@ -20,7 +20,7 @@ import torch
 from . import api, geometry
 
 RANK_CLASS_IDS = (6, 11, 16, 21, 26, 37, 43)  # *_rank classes, roadmap1.v3i.yolov8/data.yaml:6
-GPU_LAUNCHES_PER_STEP = 5                      # letterbox, decode_filter, sort_topk, nms, roi_from_detections
+GPU_LAUNCHES_PER_STEP = 6                      # letterbox, class filter, box decode, sort_topk, nms, roi_from_detections
 
 
 @dataclass
