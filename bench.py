@@ -180,7 +180,8 @@ def run_ours(args, rank, world, local):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    pipe = m.Pipeline(BATCH, SRC_HW, NC, imgsz=IMGSZ, conf=CONF, iou=IOU, max_det=MAX_DET, device=dev)
+    pipe = m.Pipeline(BATCH, SRC_HW, NC, imgsz=IMGSZ, conf=CONF, iou=IOU, max_det=MAX_DET, device=dev,
+                      cap=args.cap or None)
 
     # inputs: seeded per rank (config 5: seeds = base + rank); generated on the CPU so the oracle sees the same bits
     frames_h = synth.synth_frames(BATCH, *SRC_HW, seed=rank).pin_memory()
@@ -209,10 +210,22 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     multigpu.barrier()
     ms_eager = multigpu.max_over_ranks(e0.elapsed_time(e1), dev)
-    kt = pipe.kernel_times_ms()
+    kt_eager = pipe.kernel_times_ms()
     pipe.enable_profiling(False)
     # (b) the same step captured once into a CUDA graph and replayed: this is how the path is meant to be
-    #     driven (one launch per batch), and what `value` reports
+    #     driven (one launch per batch).  First an instrumented graph (external event nodes around every
+    #     kernel; one synchronize per replay to read them) for the per-kernel breakdown and the roofline ...
+    pipe.enable_profiling(True, external=True)
+    pipe.capture(frames_d, head_d)
+    kt = {}
+    for it in range(max(3, args.warmup) + args.steps):
+        pipe.replay()
+        torch.cuda.synchronize()
+        if it >= max(3, args.warmup):
+            for k, v in pipe.kernel_times_ms().items():
+                kt.setdefault(k, []).extend(v)
+    pipe.enable_profiling(False)
+    # ... then the plain graph, K replays back to back between barriers: this is `value`
     pipe.capture(frames_d, head_d)
     for _ in range(max(3, args.warmup)):
         pipe.replay()
@@ -248,6 +261,7 @@ def run_ours(args, rank, world, local):
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     e2e_value = total_frames / (e2e_ms / 1e3)
     n_det = int(out[1].sum())
+    max_cand = pipe.check_overflow()           # cap < A drops candidates past cap: the run is valid only if none were
 
     if rank != 0:
         return
@@ -273,7 +287,7 @@ def run_ours(args, rank, world, local):
         "decode_filter": BATCH * (64 + NC) * pipe.A * 4,
     }
     for name, v in kt.items():
-        kernels[name] = {"us": 1e3 * statistics.mean(v)}
+        kernels[name] = {"us": 1e3 * statistics.mean(v), "us_eager_launch": 1e3 * statistics.mean(kt_eager[name])}
         if name in bytes_per_launch:
             kernels[name]["algo_GBps"] = bytes_per_launch[name] / (statistics.mean(v) / 1e3) / 1e9
             kernels[name]["frac_of_measured_peak"] = kernels[name]["algo_GBps"] / peak
@@ -289,22 +303,23 @@ def run_ours(args, rank, world, local):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(world, {"launch_mode": "one CUDA-graph replay per step (5 kernels + 1 memset captured)"}),
+            "config": _config(world, {"launch_mode": "one CUDA-graph replay per step (all kernels of the step + 1 memset captured)"}),
             "value_eager_launches": value_eager,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(),
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_step(), "ms_per_step": e2e_ms / args.steps,
                     "note": "HostRunner: pinned host frames+head -> device path -> detections back, double-buffered"},
-            "gpu_launches": m.pipeline.GPU_LAUNCHES_PER_STEP * args.steps * world,   # timed (graph) region only
+            "gpu_launches": pipe.launches_per_step() * args.steps * world,   # timed (graph) region only
             "roofline": {"kernel": "letterbox_kernel<float> (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": BATCH * k1_bytes_frame, "avg_launch_us": 1e3 * k1_ms,
-                         "timed_in": "the eager instrumented pass (CUDA events around each launch, same K steps)"},
+                         "timed_in": "K CUDA-graph replays with external event nodes around each kernel"},
             "kernels": kernels,
             "pipeline_roofline": {"bytes_per_frame": pipeline_bytes_frame,
                                   "roofline_frames_per_s_per_gpu": peak * 1e9 / pipeline_bytes_frame,
                                   "frac": (value / world) / (peak * 1e9 / pipeline_bytes_frame)},
-            "cpu_baseline": cpu, "clocks": clocks, "detections_last_step": n_det}
+            "cpu_baseline": cpu, "clocks": clocks, "detections_last_step": n_det,
+            "candidates": {"cap": pipe.cap, "max_per_image": max_cand, "fused_postprocess": pipe.fused}}
     print(json.dumps(line), flush=True)
 
 
@@ -315,6 +330,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cap", type=int, default=1024,
+                    help="candidate capacity per image (<=1024 selects the fused post-processing kernel; 0 = all anchors)")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

@@ -86,6 +86,13 @@ int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels, int B, in
                            const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count,
                            int cap, void* stream);
 
+/* First half of b200yolo_decode_filter only: class reduction + confidence filter + compaction.  The rows
+ * of the survivors carry score and class (columns 4,5); their boxes are left to
+ * b200yolo_postprocess_small, which decodes them inside the fused per-image kernel. */
+int b200yolo_class_filter(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
+                          const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count,
+                          int cap, void* stream);
+
 /* Same outputs from an already decoded UL-format prediction (B, 4+nc(+extra), A): rows 0-3 xywh,
  * rows 4.. class scores.  This is the non_max_suppression(prediction, ...) drop-in entry. */
 int b200yolo_filter_decoded(const float* pred, int B, int channels, int nc, int A, float conf_thres,
@@ -115,6 +122,18 @@ int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_coun
                  const float* scale, float* out, int* out_anchor, int* out_count,
                  const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* ---- K2b+K3+K4 fused for the sparse regime (cap <= 1024 candidates per image) -------------------
+ * One launch, one CTA per image, all in shared memory: DFL box decode of the survivors (levels != NULL:
+ * rows come from b200yolo_class_filter; levels == NULL: rows already hold boxes), the K3 sort, the K4
+ * NMS with max_det, optional scale_boxes, ROI counts.  Same outputs and bit-exact same results as
+ * b200yolo_sort_topk + b200yolo_nms.  An image whose cand_count exceeds cap is processed on its first
+ * cap slots only -- the caller must size cap for its confidence threshold and check cand_count. */
+int b200yolo_postprocess_small(const b200yolo_level* levels, int n_levels, float* cand, const int* cand_anchor,
+                               const int* cand_count, int B, int cap, int max_nms, double iou_thres,
+                               float max_wh, int agnostic, int max_det, const float* scale, float* out,
+                               int* out_anchor, int* out_count, const uint32_t* roi_class_mask, int roi_nc,
+                               int* roi_cnt, void* stream);
 
 /* ---- a10: ops.scale_boxes + clip_boxes on a flat (n,>=4) xyxy array (in place) --------------- */
 int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float pad_x, float pad_y,

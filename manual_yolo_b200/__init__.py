@@ -6,7 +6,8 @@ hand-written CUDA behind the C ABI of ``include/b200yolo.h`` (``libb200yolo.so``
 
 from . import geometry  # noqa: F401
 from .api import (Candidates, Detections, Workspace, crop_resize_rois, decode_and_filter, filter_decoded,  # noqa: F401
-                  letterbox, nms_candidates, nms_sorted, non_max_suppression, preprocess, rois_from_detections, scale_boxes, scale_params_tensor,
+                  letterbox, nms_candidates, nms_sorted, non_max_suppression, postprocess_small, preprocess,
+                  rois_from_detections, scale_boxes, scale_params_tensor,
                   select_rois, sort_candidates)
 from .pipeline import HostRunner, Pipeline, PipelineResult  # noqa: F401
 

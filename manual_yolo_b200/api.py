@@ -117,16 +117,9 @@ def _alloc_candidates(B, cap, device, out: Optional[Candidates]):
                       torch.zeros((B,), dtype=torch.int32, device=device), cap)
 
 
-def decode_and_filter(head, strides=(8, 16, 32), conf_thres=0.25, classes=None, in_hw=None, level_hw=None,
-                      cap=None, out: Optional[Candidates] = None) -> Candidates:
-    """Detect-head decode + confidence filter.
-
-    ``head`` is either the concatenated (B, 64+nc, A) fp32 tensor (``Detect._inference``'s ``x_cat``;
-    give ``in_hw`` = letterboxed input (h, w) or ``level_hw``) or the list of per-level
-    (B, 64+nc, Hi, Wi) tensors straight from the Detect convolutions.
-    """
-    if not 0 <= conf_thres <= 1:
-        raise ValueError(f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0")
+def _head_levels(head, strides, in_hw, level_hw):
+    """C-ABI level descriptors for a concatenated (B,64+nc,A) head or a list of per-level tensors.
+    Returns (levels, n_levels, B, nc, A, device, keepalive)."""
     levels = (_lib.Level * 3)()
     if isinstance(head, (list, tuple)):
         if len(head) > 3 or len(head) != len(strides):
@@ -162,14 +155,55 @@ def decode_and_filter(head, strides=(8, 16, 32), conf_thres=0.25, classes=None, 
     nc = no - 4 * REG_MAX
     if nc <= 0:
         raise ValueError("head needs 64 DFL channels + nc class channels")
+    return levels, n_levels, B, nc, A, device, keep
+
+
+def decode_and_filter(head, strides=(8, 16, 32), conf_thres=0.25, classes=None, in_hw=None, level_hw=None,
+                      cap=None, out: Optional[Candidates] = None, defer_boxes=False) -> Candidates:
+    """Detect-head decode + confidence filter.
+
+    ``head`` is either the concatenated (B, 64+nc, A) fp32 tensor (``Detect._inference``'s ``x_cat``;
+    give ``in_hw`` = letterboxed input (h, w) or ``level_hw``) or the list of per-level
+    (B, 64+nc, Hi, Wi) tensors straight from the Detect convolutions.  ``defer_boxes=True`` runs the
+    class filter only: the survivors' boxes are decoded later by ``postprocess_small``.
+    """
+    if not 0 <= conf_thres <= 1:
+        raise ValueError(f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0")
+    levels, n_levels, B, nc, A, device, keep = _head_levels(head, strides, in_hw, level_hw)
     cap = int(cap or A)
     cands = _alloc_candidates(B, cap, device, out)
     mask = _class_mask(classes, nc, device)
-    rc = _lib.load().b200yolo_decode_filter(levels, n_levels, B, nc, float(conf_thres), _ptr(mask), _ptr(cands.rows),
-                                            _ptr(cands.anchor), _ptr(cands.count), cap, _stream())
+    fn = _lib.load().b200yolo_class_filter if defer_boxes else _lib.load().b200yolo_decode_filter
+    rc = fn(levels, n_levels, B, nc, float(conf_thres), _ptr(mask), _ptr(cands.rows), _ptr(cands.anchor),
+            _ptr(cands.count), cap, _stream())
     _lib.check(rc, "decode_and_filter")
     del keep
     return cands
+
+
+def postprocess_small(cands: Candidates, det: "Detections", head=None, strides=(8, 16, 32), in_hw=None, level_hw=None,
+                      iou_thres=0.45, agnostic=False, max_nms=30000, max_wh=7680, scale: Optional[torch.Tensor] = None,
+                      roi_mask: Optional[torch.Tensor] = None, roi_nc=0, roi_cnt: Optional[torch.Tensor] = None):
+    """Fused box decode + sort + NMS (+rescale) for ``cands.cap <= 1024``: one launch, one CTA per image.
+
+    ``head``: the same head passed to ``decode_and_filter(..., defer_boxes=True)`` (None if the candidate
+    rows already hold boxes).  Results are bit-identical to ``nms_candidates``.  Images whose
+    ``cands.count`` exceeds ``cands.cap`` are processed on their first ``cap`` slots only: check the counts."""
+    if not 0 <= iou_thres <= 1:
+        raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
+    B = cands.rows.shape[0]
+    max_det = det.rows.shape[1]
+    levels, n_levels, keep = None, 0, None
+    if head is not None:
+        levels, n_levels, _, _, _, _, keep = _head_levels(head, strides, in_hw, level_hw)
+    rc = _lib.load().b200yolo_postprocess_small(levels, n_levels, _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count),
+                                                B, cands.cap, int(max_nms), float(iou_thres), float(max_wh),
+                                                int(bool(agnostic)), int(max_det), _ptr(scale), _ptr(det.rows),
+                                                _ptr(det.anchor), _ptr(det.count), _ptr(roi_mask), int(roi_nc),
+                                                _ptr(roi_cnt), _stream())
+    _lib.check(rc, "postprocess_small")
+    del keep
+    return det
 
 
 def filter_decoded(prediction, conf_thres=0.25, classes=None, nc=0, cap=None,

@@ -17,22 +17,14 @@
 // HBM-bound: algorithmic bytes per frame = (64+nc)*A*4 read + 28 B per survivor written.
 // Compiled with -fmad=false: every add/mul below rounds separately, as the torch CPU ops do.
 
-#include "common.cuh"
+#include "levels.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kReg = B200YOLO_REG_MAX;
+using b200::kReg;
+using b200::Levels;
 
-struct Levels {
-  const float* ptr[B200YOLO_MAX_LEVELS];
-  long long bstride[B200YOLO_MAX_LEVELS];
-  long long cstride[B200YOLO_MAX_LEVELS];
-  int w[B200YOLO_MAX_LEVELS];
-  int off[B200YOLO_MAX_LEVELS + 1];  // anchor offsets, off[n_levels] = A
-  float stride[B200YOLO_MAX_LEVELS];
-  int n;
-};
 
 
 __device__ __forceinline__ bool class_allowed(const uint32_t* mask, int c) {
@@ -92,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L,
                                                                  const uint32_t* __restrict__ class_mask,
                                                                  float* __restrict__ cand,
                                                                  int* __restrict__ cand_anchor,
-                                                                 int* __restrict__ cand_count, int cap) {
+                                                                 int* __restrict__ cand_count, int cap, int defer) {
   __shared__ Part part[kGroups][kQ][32];
   __shared__ float dist[kGroups][kQ][32];
   __shared__ unsigned char flag[kGroups][32];
@@ -173,6 +165,10 @@ __global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L,
     flag[g][lane] = is_cand;
   }
   if (!__syncthreads_or(is_cand)) return;   // no survivor among this CTA's 64 anchors (the common case)
+  if (RAW && defer) {                        // boxes decoded later (b200yolo_class_filter)
+    if (q == 0) emit_pending(is_cand, b, a, score, cls, cand, cand_anchor, cand_count, cap);
+    return;
+  }
 
   float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
   if (RAW) {
@@ -356,44 +352,16 @@ __global__ void __launch_bounds__(256) box_decode_kernel(const Levels L, float* 
     const int slot = blk * 64 + (threadIdx.x >> 2);
     const bool act = slot < n;
     const int a = act ? cand_anchor[(int64_t)b * cap + slot] : 0;
-    int off = 0, lw = L.w[0];
-    long long cs = L.cstride[0], bs = L.bstride[0];
-    const float* base = L.ptr[0];
-    float st = L.stride[0];
-#pragma unroll
-    for (int l = 1; l < B200YOLO_MAX_LEVELS; ++l) {
-      if (l < L.n && a >= L.off[l]) {
-        off = L.off[l]; lw = L.w[l]; cs = L.cstride[l]; bs = L.bstride[l]; base = L.ptr[l]; st = L.stride[l];
-      }
-    }
-    const int i = a - off;
-    const float* p = base + (long long)b * bs + i + (long long)(sd * kReg) * cs;
-    float d = 0.f;
-    if (act) {
-      float v[kReg];
-#pragma unroll
-      for (int k = 0; k < kReg; ++k) v[k] = p[(long long)k * cs];
-      float mx = v[0];
-#pragma unroll
-      for (int k = 1; k < kReg; ++k) mx = fmaxf(mx, v[k]);
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < kReg; ++k) { v[k] = b200::expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
-#pragma unroll
-      for (int k = 0; k < kReg; ++k) d = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), d);   // torch's conv: sequential fma
-    }
+    const b200::AnchorRef r = b200::anchor_ref(L, b, a);
+    const float d = act ? b200::dfl_side(r.p + (long long)(sd * kReg) * r.cs, r.cs) : 0.f;
     const int q0 = lane & ~3;
     const float d0 = __shfl_sync(0xffffffffu, d, q0), d1 = __shfl_sync(0xffffffffu, d, q0 + 1);
     const float d2 = __shfl_sync(0xffffffffu, d, q0 + 2), d3 = __shfl_sync(0xffffffffu, d, q0 + 3);
     if (act && sd == 0) {
-      const float ax = (float)(i % lw) + 0.5f, ay = (float)(i / lw) + 0.5f;
-      const float bx1 = ax - d0, by1 = ay - d1, bx2 = ax + d2, by2 = ay + d3;
-      const float cx = ((bx1 + bx2) / 2.0f) * st, cy = ((by1 + by2) / 2.0f) * st;
-      const float bw = (bx2 - bx1) * st, bh = (by2 - by1) * st;
-      const float hw = bw / 2.0f, hh = bh / 2.0f;
+      const float4 bx = b200::decode_box(r, d0, d1, d2, d3);
       float2* row = reinterpret_cast<float2*>(cand + ((int64_t)b * cap + slot) * 6);
-      row[0] = make_float2(cx - hw, cy - hh);
-      row[1] = make_float2(cx + hw, cy + hh);
+      row[0] = make_float2(bx.x, bx.y);
+      row[1] = make_float2(bx.z, bx.w);
     }
   }
 }
@@ -401,7 +369,7 @@ __global__ void __launch_bounds__(256) box_decode_kernel(const Levels L, float* 
 // Try the vectorised path; returns -1000 if the shape is not eligible (caller falls back to the scalar kernel).
 template <bool RAW>
 static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, const uint32_t* class_mask, float* cand,
-                      int* cand_anchor, int* cand_count, int cap, cudaStream_t stream) {
+                      int* cand_anchor, int* cand_count, int cap, bool defer_boxes, cudaStream_t stream) {
   const int A = L.off[B200YOLO_MAX_LEVELS];
   FlatSegs S;
   // one flat segment if the levels are views of one concatenated tensor, else one per level
@@ -425,7 +393,7 @@ static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, cons
   }
   dim3 grid((unsigned)((maxcount + kVA - 1) / kVA), B, S.n);
   decode_vec_kernel<RAW><<<grid, 256, 0, stream>>>(S, L, nc, cls0, conf, class_mask, cand, cand_anchor, cand_count, cap);
-  if (RAW) {
+  if (RAW && !defer_boxes) {
     const int amax = cap < A ? cap : A;               // an image has at most min(cap, A) stored survivors
     const int per_image = (amax + 63) / 64;           // blocks of 64 survivors; CTAs grid-stride over them
     const int want = (4 * B200_NUM_SMS + B - 1) / B;  // enough CTAs to fill the GPU when every anchor survives
@@ -437,40 +405,41 @@ static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, cons
 
 }  // namespace
 
-extern "C" int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
-                                      const uint32_t* class_mask, float* cand, int* cand_anchor,
-                                      int* cand_count, int cap, void* stream) {
+static int decode_filter_impl(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
+                              const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count, int cap,
+                              bool defer_boxes, void* stream) {
   B200_REQUIRE(levels && cand && cand_anchor && cand_count, B200YOLO_ERR_NULL);
-  B200_REQUIRE(n_levels >= 1 && n_levels <= B200YOLO_MAX_LEVELS, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(B > 0 && B <= 65535 && nc > 0 && cap > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(nc <= B200YOLO_MAX_CLASSES, B200YOLO_ERR_UNSUPPORTED);
   B200_REQUIRE(conf_thres >= 0.f && conf_thres <= 1.f, B200YOLO_ERR_RANGE);
   Levels L;
-  L.n = n_levels;
-  long long off = 0;
-  for (int l = 0; l < B200YOLO_MAX_LEVELS; ++l) {
-    if (l < n_levels) {
-      B200_REQUIRE(levels[l].ptr, B200YOLO_ERR_NULL);
-      B200_REQUIRE(levels[l].h > 0 && levels[l].w > 0 && levels[l].stride > 0.f, B200YOLO_ERR_SHAPE);
-      B200_REQUIRE((reinterpret_cast<uintptr_t>(levels[l].ptr) & 3) == 0, B200YOLO_ERR_ALIGN);
-      L.ptr[l] = levels[l].ptr; L.bstride[l] = levels[l].batch_stride; L.cstride[l] = levels[l].chan_stride;
-      L.w[l] = levels[l].w; L.stride[l] = levels[l].stride; L.off[l] = (int)off;
-      off += (long long)levels[l].h * levels[l].w;
-    } else {
-      L.ptr[l] = nullptr; L.bstride[l] = 0; L.cstride[l] = 0; L.w[l] = 1; L.stride[l] = 1.f; L.off[l] = (int)off;
-    }
-  }
-  B200_REQUIRE(off <= (1LL << 30), B200YOLO_ERR_UNSUPPORTED);
-  for (int l = n_levels; l <= B200YOLO_MAX_LEVELS; ++l) L.off[l] = (int)off;
+  const int st = b200::build_levels(levels, n_levels, L);
+  if (st != B200YOLO_OK) return st;
+  const int A = L.off[B200YOLO_MAX_LEVELS];
   {
     const int rc = launch_vec<true>(L, B, nc, 4 * kReg, conf_thres, class_mask, cand, cand_anchor, cand_count, cap,
-                                    (cudaStream_t)stream);
+                                    defer_boxes, (cudaStream_t)stream);
     if (rc != -1000) return rc;
   }
-  dim3 grid((unsigned)((off + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
+  dim3 grid((unsigned)((A + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
   decode_filter_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, nullptr, 0, nc, conf_thres, class_mask,
-                                                                           cand, cand_anchor, cand_count, cap);
+                                                                           cand, cand_anchor, cand_count, cap,
+                                                                           defer_boxes ? 1 : 0);
   return b200_launch_status();
+}
+
+extern "C" int b200yolo_decode_filter(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
+                                      const uint32_t* class_mask, float* cand, int* cand_anchor,
+                                      int* cand_count, int cap, void* stream) {
+  return decode_filter_impl(levels, n_levels, B, nc, conf_thres, class_mask, cand, cand_anchor, cand_count, cap, false,
+                            stream);
+}
+
+extern "C" int b200yolo_class_filter(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
+                                     const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count,
+                                     int cap, void* stream) {
+  return decode_filter_impl(levels, n_levels, B, nc, conf_thres, class_mask, cand, cand_anchor, cand_count, cap, true,
+                            stream);
 }
 
 extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, int nc, int A, float conf_thres,
@@ -489,13 +458,13 @@ extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, i
   }
   L.off[B200YOLO_MAX_LEVELS] = A;
   {
-    const int rc = launch_vec<false>(L, B, nc, 4, conf_thres, class_mask, cand, cand_anchor, cand_count, cap,
+    const int rc = launch_vec<false>(L, B, nc, 4, conf_thres, class_mask, cand, cand_anchor, cand_count, cap, false,
                                      (cudaStream_t)stream);
     if (rc != -1000) return rc;
   }
   dim3 grid((unsigned)((A + kAnchorsPerCta - 1) / kAnchorsPerCta), B);
   decode_filter_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, pred, channels, nc, conf_thres,
                                                                             class_mask, cand, cand_anchor, cand_count,
-                                                                            cap);
+                                                                            cap, 0);
   return b200_launch_status();
 }

@@ -20,6 +20,7 @@ import torch
 from . import api, geometry
 
 RANK_CLASS_IDS = (6, 11, 16, 21, 26, 37, 43)  # *_rank classes, roadmap1.v3i.yolov8/data.yaml:6
+FUSED_CAP_MAX = 1024                           # b200yolo_postprocess_small envelope
 GPU_LAUNCHES_PER_STEP = 6                      # letterbox, class filter, box decode, sort_topk, nms, roi_from_detections
 
 
@@ -54,6 +55,7 @@ class Pipeline:
         self.level_hw = geometry.level_shapes(g["out_h"], g["out_w"], strides)
         self.A = sum(h * w for h, w in self.level_hw)
         self.cap = int(cap or self.A)
+        self.fused = self.cap <= FUSED_CAP_MAX       # sparse regime: fused per-image post-processing kernel
         dev = self.device
         B = self.B
         self.net_in = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=dev)
@@ -85,14 +87,26 @@ class Pipeline:
         t("letterbox")
         api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
                        out=self.net_in)
-        t("decode_filter")
-        api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
-                              cap=self.cap, out=self.cands)
-        t("sort_topk")
-        api.sort_candidates(self.cands, self.max_nms, self.ws)
-        t("nms")
-        det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
-                             scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
+        if self.fused:
+            # sparse regime (cap <= 1024): class filter, then ONE fused launch for decode + sort + NMS
+            t("decode_filter")
+            api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
+                                  cap=self.cap, out=self.cands, defer_boxes=True)
+            t("postprocess_small")
+            det = api.postprocess_small(self.cands, self.ws.det, head, self.strides, level_hw=self.level_hw,
+                                        iou_thres=self.iou, agnostic=self.agnostic, max_nms=self.max_nms,
+                                        max_wh=self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
+                                        roi_cnt=self.roi_cnt)
+        else:
+            t("decode_filter")
+            api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
+                                  cap=self.cap, out=self.cands)
+            t("sort_topk")
+            api.sort_candidates(self.cands, self.max_nms, self.ws)
+            t("nms")
+            det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms,
+                                 self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
+                                 roi_cnt=self.roi_cnt)
         t("roi_crop_resize")
         ro = api.rois_from_detections(frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
@@ -100,14 +114,17 @@ class Pipeline:
         return PipelineResult(self.net_in, det, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
 
     # -- per-kernel CUDA-event timing (bench.py): events on the launching stream around each stage --
-    def enable_profiling(self, on=True):
+    def enable_profiling(self, on=True, external=False):
+        """``external=True`` records the events as external nodes so they can sit inside a captured CUDA
+        graph: after ``capture()`` every ``replay()`` + synchronize refreshes ``kernel_times_ms()``."""
         self._prof = [] if on else None
         self._open = None
+        self._prof_external = bool(external)
 
     def _tick(self, name):
         if getattr(self, "_prof", None) is None:
             return
-        ev = torch.cuda.Event(enable_timing=True)
+        ev = torch.cuda.Event(enable_timing=True, external=getattr(self, "_prof_external", False))
         ev.record()
         if self._open is not None:
             self._prof.append((self._open[0], self._open[1], ev))
@@ -131,6 +148,8 @@ class Pipeline:
             self(frames, head)                       # warm-up: sets kernel attributes, touches buffers
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if self._prof is not None:
+            self._prof, self._open = [], None        # keep only the events recorded inside the graph
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._result = self(frames, head)
@@ -156,6 +175,19 @@ class Pipeline:
         h_count.copy_(res.det.count, non_blocking=True)
         h_roi.copy_(res.roi_count, non_blocking=True)
         return h_rows, h_count, h_roi
+
+    def launches_per_step(self):
+        """Kernels of this package launched per step (class filter [+ box decode, sort, nms | fused], letterbox, roi)."""
+        return 4 if self.fused else 6
+
+    def check_overflow(self):
+        """Raise if any image of the last step had more candidates than ``cap`` (one D2H of the counts).
+        With ``cap < A`` a candidate beyond ``cap`` is dropped, so results are only valid when this passes."""
+        mx = int(self.cands.count.max())
+        if mx > self.cap:
+            raise RuntimeError(f"candidate overflow: {mx} candidates in one image > cap={self.cap}; "
+                               "raise cap (cap=None uses all anchors) or the confidence threshold")
+        return mx
 
     def make_staging(self):
         dev = self.device

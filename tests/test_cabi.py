@@ -19,7 +19,7 @@ def _declared_symbols():
 def test_header_symbols_exported_and_bound():
     lib = _lib.load()
     names = _declared_symbols()
-    assert len(names) >= 13
+    assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), f"{n} declared in b200yolo.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
@@ -49,6 +49,8 @@ def test_argument_errors_before_any_launch():
     assert lib.b200yolo_sort_topk(one, one, one, 1, 70000, 30000, one, null, 0, null) == -4
     assert lib.b200yolo_sort_topk(one, one, one, 1, 20000, 30000, one, null, 0, null) == -1   # needs workspace
     assert lib.b200yolo_roi_crop_resize(one, 1, 8, 8, 24, 192, one, one, null, 4, 6, 128, one, one, null) == -4
+    assert lib.b200yolo_postprocess_small(None, 0, one, one, one, 1, 2048, 30000, 0.5, 7680.0, 0, 300, null, one, one, one,
+                                          null, 0, null, null) == -4
     assert lib.b200yolo_workspace_bytes(4, 8400) == 16
     assert lib.b200yolo_workspace_bytes(4, 20000) == 4 * (20000 + 1250) * 16
     with pytest.raises(ValueError):
