@@ -225,7 +225,23 @@ def run_ours(args, rank, world, local):
             for k, v in pipe.kernel_times_ms().items():
                 kt.setdefault(k, []).extend(v)
     pipe.enable_profiling(False)
-    # ... then the plain graph, K replays back to back between barriers: this is `value`
+    # serial (single-stream) graph, K replays: reported as value_serial_graph
+    pipe.capture(frames_d, head_d)
+    for _ in range(max(3, args.warmup)):
+        pipe.replay()
+    torch.cuda.synchronize()
+    multigpu.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        pipe.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_serial = multigpu.max_over_ranks(e0.elapsed_time(e1), dev)
+    # ... then the production graph: the letterbox branch (HBM-bound) forked onto a side stream so that it
+    # runs concurrently with the decode -> NMS -> ROI branch (latency-bound); K replays back to back between
+    # barriers: this is `value`
+    pipe.overlap = True
+    pipe._side = torch.cuda.Stream(device=dev)
     pipe.capture(frames_d, head_d)
     for _ in range(max(3, args.warmup)):
         pipe.replay()
@@ -243,6 +259,7 @@ def run_ours(args, rank, world, local):
     total_frames = BATCH * args.steps * world
     value = total_frames / (ms_max / 1e3)
     value_eager = total_frames / (ms_eager / 1e3)
+    value_serial = total_frames / (ms_serial / 1e3)
 
     # ---- end to end on host buffers (H2D frames+head, D2H detections, every step) ----
     runner = m.HostRunner(pipe, depth=2)
@@ -303,8 +320,8 @@ def run_ours(args, rank, world, local):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(world, {"launch_mode": "one CUDA-graph replay per step (all kernels of the step + 1 memset captured)"}),
-            "value_eager_launches": value_eager,
+            "config": _config(world, {"launch_mode": "one CUDA-graph replay per step; letterbox forked onto a side stream, concurrent with decode->NMS->ROI of the same batch"}),
+            "value_eager_launches": value_eager, "value_serial_graph": value_serial,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(),
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_step(), "ms_per_step": e2e_ms / args.steps,
                     "note": "HostRunner: pinned host frames+head -> device path -> detections back, double-buffered"},
@@ -313,7 +330,7 @@ def run_ours(args, rank, world, local):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": BATCH * k1_bytes_frame, "avg_launch_us": 1e3 * k1_ms,
-                         "timed_in": "K CUDA-graph replays with external event nodes around each kernel"},
+                         "timed_in": "K single-stream CUDA-graph replays with external event nodes around each kernel (kernels serialised, no overlap)"},
             "kernels": kernels,
             "pipeline_roofline": {"bytes_per_frame": pipeline_bytes_frame,
                                   "roofline_frames_per_s_per_gpu": peak * 1e9 / pipeline_bytes_frame,

@@ -39,7 +39,7 @@ class PipelineResult:
 class Pipeline:
     def __init__(self, batch: int, src_hw, nc: int, imgsz=640, auto=False, conf=0.25, iou=0.7, max_det=300,
                  agnostic=False, classes=None, max_nms=30000, max_wh=7680, roi_classes: Sequence[int] = RANK_CLASS_IDS,
-                 rois_per_frame=8, pad=6, roi_size=64, strides=(8, 16, 32), device="cuda", cap=None):
+                 rois_per_frame=8, pad=6, roi_size=64, strides=(8, 16, 32), device="cuda", cap=None, overlap=False):
         if not torch.cuda.is_available():
             raise RuntimeError("manual_yolo_b200.Pipeline needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -77,6 +77,11 @@ class Pipeline:
         self._static = None
         self._prof = None
         self._open = None
+        # overlap=True: the letterbox kernel (HBM-bound, feeds the backbone) runs on a side stream,
+        # concurrently with decode -> NMS -> ROI of the same batch (latency-bound, feed the classifier);
+        # the two branches share no buffer.  Fork/join with events, capturable into one CUDA graph.
+        self.overlap = bool(overlap)
+        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
 
     # -- one step on device-resident inputs ------------------------------------------------------
     def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
@@ -84,9 +89,16 @@ class Pipeline:
         if tuple(frames.shape) != (self.B, self.src_hw[0], self.src_hw[1], 3):
             raise ValueError(f"frames must be {(self.B, *self.src_hw, 3)}, got {tuple(frames.shape)}")
         t = self._tick
-        t("letterbox")
-        api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
-                       out=self.net_in)
+        if self.overlap:
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)                               # fork
+            with torch.cuda.stream(self._side):
+                api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
+                               out=self.net_in)
+        else:
+            t("letterbox")
+            api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
+                           out=self.net_in)
         if self.fused:
             # sparse regime (cap <= 1024): class filter, then ONE fused launch for decode + sort + NMS
             t("decode_filter")
@@ -111,6 +123,8 @@ class Pipeline:
         ro = api.rois_from_detections(frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
         t(None)
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self._side)        # join
         return PipelineResult(self.net_in, det, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
 
     # -- per-kernel CUDA-event timing (bench.py): events on the launching stream around each stage --

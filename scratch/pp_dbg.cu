@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
                                                                const float* __restrict__ scale, float* __restrict__ out,
                                                                int* __restrict__ out_anchor, int* __restrict__ out_count,
                                                                const uint32_t* __restrict__ roi_mask, int roi_nc,
-                                                               int* __restrict__ roi_cnt) {
+                                                               int* __restrict__ roi_cnt, long long* dbg) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  long long T[12]; int ti=0; T[ti++]=clock64();
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   int* keep = reinterpret_cast<int*>(smem_raw + ((sizeof(Smem) + 15) & ~(size_t)15));   // [max_det]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
   if (tid == 0) { sm.kcount = 0; sm.roi = 0; }
   __syncthreads();
 
+  T[ti++]=clock64();
   // ---- (2) DFL box decode of the survivors: 4 lanes per candidate (lane = side), one load round ----
   if (decode) {
     for (int base = 0; base < n; base += NT / 4) {
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
     }
   }
 
+  T[ti++]=clock64();
   // ---- (3) sort: score descending, anchor ascending on ties (64-bit composite keys) ----
   uint64_t* src = sm.u.keys.a;
   uint64_t* dst = sm.u.keys.b;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
     __syncthreads();
   }
 
+  T[ti++]=clock64();
   // ---- (4) class-offset boxes in sorted order (the key buffers are dead now) ----
   for (int r = tid; r < n_nms; r += NT) {
     const float* row = sm.rows[sm.order[r]];
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
   }
   __syncthreads();
 
+  T[ti++]=clock64();
   // ---- (5) greedy NMS in chunks of 64 (as nms.cu) ----
   const float4* box = sm.u.box;
   for (int s = 0; s < n_nms; s += kChunk) {
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
   }
   __syncthreads();
 
+  T[ti++]=clock64();
   // ---- (6) outputs: un-offset rows in kept order, optional scale_boxes + clip, ROI count ----
   const int kc = sm.kcount;
   float gain = 1.f, padx = 0.f, pady = 0.f, w0 = 0.f, h0 = 0.f;
@@ -304,16 +310,17 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
     }
   }
   __syncthreads();
-  if (tid == 0) { out_count[b] = kc; if (roi_cnt) roi_cnt[b] = sm.roi; }
+  T[ti++]=clock64();
+  if (tid == 0) { out_count[b] = kc; if (roi_cnt) roi_cnt[b] = sm.roi; for(int q=0;q<ti;q++) dbg[b*12+q]=T[q]-T[0]; dbg[b*12+11]=n; }
 }
 
 }  // namespace
 
-extern "C" int b200yolo_postprocess_small(const b200yolo_level* levels, int n_levels, float* cand,
+extern "C" int dbg_postprocess_small(const b200yolo_level* levels, int n_levels, float* cand,
                                           const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
                                           double iou_thres, float max_wh, int agnostic, int max_det,
                                           const float* scale, float* out, int* out_anchor, int* out_count,
-                                          const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* stream) {
+                                          const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* stream, void* dbgptr) {
   B200_REQUIRE(cand && cand_anchor && cand_count && out && out_anchor && out_count, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && cap > 0 && max_nms > 0 && max_det > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(cap <= kCapMax && max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
@@ -336,6 +343,6 @@ extern "C" int b200yolo_postprocess_small(const b200yolo_level* levels, int n_le
   if (e != cudaSuccess) return (int)e;
   postprocess_small_kernel<<<B, NT, smem, (cudaStream_t)stream>>>(L, decode, cand, cand_anchor, cand_count, cap, max_nms,
                                                                   iou_thres, max_wh, agnostic, max_det, scale, out,
-                                                                  out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt);
+                                                                  out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, (long long*)dbgptr);
   return b200_launch_status();
 }

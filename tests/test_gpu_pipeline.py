@@ -86,6 +86,14 @@ def test_graph_replay_and_host_entry(cuda_dev):
     res = pipe.replay()
     torch.cuda.synchronize()
     _assert_matches(res, ref, B)
+    # overlap mode: letterbox on a side stream (fork/join), eager and captured -- same results
+    pipe2 = m.Pipeline(B, src_hw, nc, imgsz=320, conf=0.25, iou=0.7, device=cuda_dev, cap=1024, overlap=True)
+    _assert_matches(pipe2(d_frames, d_head), ref, B)
+    pipe2.capture(d_frames, d_head)
+    pipe2.net_in.zero_()
+    res2 = pipe2.replay()
+    torch.cuda.synchronize()
+    _assert_matches(res2, ref, B)
     # host-facing entry: pinned host buffers in, host results out
     rows, count, nroi = pipe.run_host(frames.pin_memory(), head.pin_memory())
     torch.cuda.synchronize()
