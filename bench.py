@@ -241,7 +241,7 @@ def run_ours(args, rank, world, local):
     # runs concurrently with the decode -> NMS -> ROI branch (latency-bound); K replays back to back between
     # barriers: this is `value`
     pipe.overlap = True
-    pipe._side = torch.cuda.Stream(device=dev)
+    pipe._make_streams()
     pipe.capture(frames_d, head_d)
     for _ in range(max(3, args.warmup)):
         pipe.replay()

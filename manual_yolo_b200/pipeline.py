@@ -81,7 +81,15 @@ class Pipeline:
         # concurrently with decode -> NMS -> ROI of the same batch (latency-bound, feed the classifier);
         # the two branches share no buffer.  Fork/join with events, capturable into one CUDA graph.
         self.overlap = bool(overlap)
-        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        self._side = self._hi = None
+        if self.overlap:
+            self._make_streams()
+
+    def _make_streams(self):
+        # K1 on a normal-priority stream, the latency-bound branch on a HIGH-priority one: its small CTAs are
+        # scheduled first whenever an SM frees resources, so they run in the shadow of the streaming kernel
+        self._side = torch.cuda.Stream(device=self.device, priority=0)
+        self._hi = torch.cuda.Stream(device=self.device, priority=-1)
 
     # -- one step on device-resident inputs ------------------------------------------------------
     def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
@@ -92,13 +100,23 @@ class Pipeline:
         if self.overlap:
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)                               # fork
+            self._hi.wait_stream(main)
             with torch.cuda.stream(self._side):
                 api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
                                out=self.net_in)
+            with torch.cuda.stream(self._hi):
+                res = self._post_branch(frames, head, t)
+            main.wait_stream(self._side)                               # join
+            main.wait_stream(self._hi)
+            return res
         else:
             t("letterbox")
             api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
                            out=self.net_in)
+        return self._post_branch(frames, head, t)
+
+    def _post_branch(self, frames, head, t):
+        """decode -> (sort ->) NMS -> ROI crops on the current stream."""
         if self.fused:
             # sparse regime (cap <= 1024): class filter, then ONE fused launch for decode + sort + NMS
             t("decode_filter")
@@ -123,8 +141,6 @@ class Pipeline:
         ro = api.rois_from_detections(frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
         t(None)
-        if self.overlap:
-            torch.cuda.current_stream().wait_stream(self._side)        # join
         return PipelineResult(self.net_in, det, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
 
     # -- per-kernel CUDA-event timing (bench.py): events on the launching stream around each stage --
