@@ -184,8 +184,9 @@ def run_ours(args, rank, world, local):
                       cap=args.cap or None)
 
     # inputs: seeded per rank (config 5: seeds = base + rank); generated on the CPU so the oracle sees the same bits
-    frames_h = synth.synth_frames(BATCH, *SRC_HW, seed=rank).pin_memory()
-    head_h, _ = synth.synth_head_from_labels(BATCH, NC, in_hw=pipe.in_hw, src_hw=SRC_HW, seed=rank, conf_thres=CONF)
+    frames_h = synth.synth_frames(BATCH, *SRC_HW, seed=args.seed + rank).pin_memory()
+    head_h, _ = synth.synth_head_from_labels(BATCH, NC, in_hw=pipe.in_hw, src_hw=SRC_HW, seed=args.seed + rank,
+                                             conf_thres=CONF)
     head_h = head_h.pin_memory()
     frames_d, head_d = frames_h.to(dev), head_h.to(dev)
 
@@ -256,6 +257,7 @@ def run_ours(args, rank, world, local):
     t1 = time.time()
     ms = e0.elapsed_time(e1)
     ms_max = multigpu.max_over_ranks(ms, dev)
+    print(f"[rank {rank}] timed region: {ms:.4f} ms for {args.steps} steps (max over ranks {ms_max:.4f})", file=sys.stderr)
     total_frames = BATCH * args.steps * world
     value = total_frames / (ms_max / 1e3)
     value_eager = total_frames / (ms_eager / 1e3)
@@ -347,6 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0, help="base seed of the synthetic inputs (rank is added)")
     ap.add_argument("--cap", type=int, default=1024,
                     help="candidate capacity per image (<=1024 selects the fused post-processing kernel; 0 = all anchors)")
     args = ap.parse_args()
@@ -355,7 +358,7 @@ def main():
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
     from manual_yolo_b200 import multigpu
-    rank, world, local = multigpu.init_from_env("nccl")
+    rank, world, local = multigpu.init_from_env(os.environ.get("B200_DIST_BACKEND", "nccl"))
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     try:

@@ -359,8 +359,9 @@ def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=No
     """Batched ``safe_crop`` + classifier preprocessing: returns ((N,3,size,size) fp32 RGB, valid (N,) i32).
 
     ``boxes_xyxy``: (N,4) fp32 source-pixel boxes (``int()`` truncation happens on the device, as
-    ``detect.py:581`` does on the host); ``batch_idx``: (N,) int32 frame index.  ``valid`` is 0 where
-    ``safe_crop`` would return None and -1 where the ROI is larger than the kernel's envelope.
+    ``detect.py:581`` does on the host); ``batch_idx``: (N,) int32 frame index.  ``valid`` is 1 (or 2: produced by the split
+    large-ROI launch) for a valid crop, 0 where ``safe_crop`` would return None and -1 where the ROI is larger
+    than the kernel's envelope (short side > 31 x size).
     """
     frames, _ = _frames_4d(frames)
     _require_cuda(boxes_xyxy, "boxes_xyxy", torch.float32)

@@ -28,11 +28,14 @@ constexpr int kMaxTaps = 64;     // ksize = ceil(support)*2+1 <= 64  <=> scale <
 constexpr int kFastTaps = 8;     // taps kept in registers (scale <= 3.5: every rank-card crop)
 constexpr int kRowsMax = 128;    // uint8 strip rows staged per vertical tile (>= kMaxTaps)
 constexpr int kPrec = 22;        // Pillow PRECISION_BITS = 32 - 8 - 2
+constexpr int kBigArea = 160 * 160;  // crop pixels beyond which an ROI goes to the split (large-ROI) launch
+constexpr int kBigParts = 8;     // CTAs per large ROI: each produces kS/kBigParts output rows
+constexpr int kBigCtas = 32;     // large-ROI launch width (grid-strides over the deferred list)
 constexpr int kStageBytes = 48 * 1024;  // staged crop rows (a 115x105 rank crop needs ~37 KB)
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for output index `o` (triangle filter):
 // returns xmin, writes `cnt` fixed-point weights.
-__device__ int pil_axis(int o, int in_size, int out_size, int* coef, int& cnt_out) {
+__device__ int pil_axis(int o, int in_size, int out_size, int* coef, int cstride, int& cnt_out) {
   const double scale = __ddiv_rn((double)in_size, (double)out_size);
   const double fscale = scale < 1.0 ? 1.0 : scale;
   const double support = fscale;  // bilinear support 1.0 * filterscale
@@ -56,7 +59,7 @@ __device__ int pil_axis(int o, int in_size, int out_size, int* coef, int& cnt_ou
     if (v < 0.0) v = -v;
     double w = v < 1.0 ? __dsub_rn(1.0, v) : 0.0;
     if (ww != 0.0) w = __ddiv_rn(w, ww);
-    coef[x] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrec))));
+    coef[x * cstride] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrec))));
   }
   cnt_out = xmax;
   return xmin;
@@ -76,7 +79,7 @@ __device__ __forceinline__ int half_round_even(int d) {
 struct RoiSmem {
   int xb[kS][2];                 // horizontal bounds (xmin, count) per surviving output column
   int yb[kS][2];                 // vertical bounds per surviving output row
-  int xk[kS][kFastTaps];         // horizontal weights, fast path (count <= kFastTaps)
+  int xkT[kMaxTaps][kS];         // horizontal weights, transposed: xkT[tap][column] (conflict-free per warp)
   int yk[kS][kMaxTaps];          // vertical weights (broadcast reads)
   uint8_t strip[kRowsMax][3][kS];  // horizontal-pass output, uint8 like Pillow's intermediate image
   int sel[4];
@@ -98,8 +101,9 @@ __device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* a, const ui
 __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B, int H, int W, int64_t pitch,
                          int64_t bstride,
                          int bi, int bx1, int by1, int bx2, int by2, int pad, float* __restrict__ out,
-                         int* __restrict__ valid_out, RoiSmem& sm) {
+                         int* __restrict__ valid_out, RoiSmem& sm, int part, int nparts) {
   const int tid = threadIdx.x;
+  const int y_begin = part * (kS / nparts), y_end = y_begin + kS / nparts;   // this CTA's output rows
   const int rp = tid / kCols, tcol = tid % kCols;
   const int c = tcol / kS, xx = tcol % kS;     // warp = 32 consecutive columns of one channel, one row phase
   // ---- safe_crop (detect.py:100-113) ----
@@ -118,116 +122,83 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
     if (2 * (int)ceil(smx) + 1 > kMaxTaps) { ok = false; unsupported = true; }
   }
   if (!ok) {
-    for (int i = tid; i < 3 * kS * kS; i += kThreads) out[i] = 0.f;
-    if (tid == 0) *valid_out = unsupported ? -1 : 0;
+    for (int c2 = 0; c2 < 3; ++c2)
+      for (int i = tid; i < (y_end - y_begin) * kS; i += kThreads) out[(c2 * kS + y_begin) * kS + i] = 0.f;
+    if (tid == 0 && part == 0) *valid_out = unsupported ? -1 : 0;
+    return;
+  }
+  if (nparts == 1 && (int64_t)cw * ch > kBigArea) {
+    // large ROI (far beyond a rank card): deferred to roi_big_kernel, which splits it over kBigParts CTAs so
+    // that one outlier cannot stall the batch; marked valid = 2 ("valid, produced by the large-ROI launch")
+    if (tid == 0) *valid_out = 2;
     return;
   }
   const int left = half_round_even(new_w - kS), top = half_round_even(new_h - kS);
 
-  // ---- coefficient tables: threads 0..63 horizontal (own column), 64..127 vertical ----
-  int kx_big[kMaxTaps];                         // only touched when a column has > kFastTaps taps (local mem)
+  // ---- coefficient tables: threads 0..63 horizontal (own column), 64.. vertical (this CTA's rows only) ----
   if (tid < kS) {
     int cnt;
-    const int xmin = pil_axis(left + tid, cw, new_w, kx_big, cnt);
-    sm.xb[tid][0] = xmin; sm.xb[tid][1] = cnt;
-    if (cnt <= kFastTaps)
-      for (int x = 0; x < kFastTaps; ++x) sm.xk[tid][x] = x < cnt ? kx_big[x] : 0;
-  } else if (tid < 2 * kS) {
+    const int xm = pil_axis(left + tid, cw, new_w, &sm.xkT[0][tid], kS, cnt);
+    sm.xb[tid][0] = xm; sm.xb[tid][1] = cnt;
+  } else if (tid < kS + (y_end - y_begin)) {
+    const int yy = y_begin + (tid - kS);
     int cnt;
-    const int ymin = pil_axis(top + (tid - kS), ch, new_h, sm.yk[tid - kS], cnt);
-    sm.yb[tid - kS][0] = ymin; sm.yb[tid - kS][1] = cnt;
+    const int ymin = pil_axis(top + yy, ch, new_h, sm.yk[yy], 1, cnt);
+    sm.yb[yy][0] = ymin; sm.yb[yy][1] = cnt;
   }
   __syncthreads();
   const int xmin = sm.xb[xx][0], xcnt = sm.xb[xx][1];
   const bool fast_x = xcnt <= kFastTaps;
   int kx[kFastTaps];
 #pragma unroll
-  for (int x = 0; x < kFastTaps; ++x) kx[x] = fast_x ? sm.xk[xx][x] : 0;
-  if (!fast_x && tid >= kS) {                   // big ROI: every thread of the column needs the long table
-    int cnt;
-    pil_axis(left + xx, cw, new_w, kx_big, cnt);
-  }
+  for (int x = 0; x < kFastTaps; ++x) kx[x] = (x < xcnt) ? sm.xkT[x][xx] : 0;
 
   const uint8_t* crop = frames + (int64_t)bi * bstride + (int64_t)cy1 * pitch + (int64_t)cx1 * 3;
-  const uint8_t* col = crop + (int64_t)xmin * 3 + c;
   // horizontal span of source columns the 64 surviving output columns reference
   const int x_lo = sm.xb[0][0];
   const int span_bytes = (sm.xb[kS - 1][0] + sm.xb[kS - 1][1] - x_lo) * 3;
   const int row_words = (span_bytes + 3 + 3) / 4;            // any 4-byte phase fits
   const int row_stride = row_words * 4;
-  int t0 = 0;
-  while (t0 < kS) {
-    // vertical tile [t0, t1): input rows [rmin, rmax) must fit the strip
+  const int stage_rows = kStageBytes / row_stride;            // rows of this ROI one stage fill can hold (>= 1)
+  const int cofs = (xmin - x_lo) * 3 + c;
+  int t0 = y_begin;
+  while (t0 < y_end) {
+    // vertical tile [t0, t1): the input rows [rmin, rmin+rows) it references must fit the uint8 strip
     const int rmin = sm.yb[t0][0];
     int t1 = t0 + 1;
-    while (t1 < kS && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kRowsMax) ++t1;
+    while (t1 < y_end && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kRowsMax) ++t1;
     const int rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
-    const bool staged = rows * row_stride <= kStageBytes;      // CTA-uniform
-    if (staged) {
-      // ---- stage the referenced crop rows: coalesced 32-bit loads, all in flight at once ----
-      for (int e = tid; e < rows * row_words; e += kThreads) {
+    // ---- horizontal pass, stage-sized row chunks: coalesced 32-bit loads (all in flight at once) into the
+    //      stage, then every thread resamples its column for the chunk's rows ----
+    for (int r0 = 0; r0 < rows; r0 += stage_rows) {
+      const int nr = min(stage_rows, rows - r0);
+      if (r0 > 0) __syncthreads();                            // previous chunk fully consumed
+      for (int e = tid; e < nr * row_words; e += kThreads) {
         const int rr = e / row_words, wd = e - rr * row_words;
-        const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+        const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
         const uint8_t* ga = g - (reinterpret_cast<uintptr_t>(g) & 3) + wd * 4;
         reinterpret_cast<uint32_t*>(sm.stage + rr * row_stride)[wd] = load_word_guarded(ga, frames, buf_hi);
       }
       __syncthreads();
-      const int cofs = (xmin - x_lo) * 3 + c;
       if (fast_x) {
-        for (int rr = rp; rr < rows; rr += kRowPar) {
-          const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+        for (int rr = rp; rr < nr; rr += kRowPar) {
+          const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
           const uint8_t* p = sm.stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + cofs;
           int acc = 1 << (kPrec - 1);
 #pragma unroll
           for (int x = 0; x < kFastTaps; ++x)
             if (x < xcnt) acc += (int)p[x * 3] * kx[x];
-          sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
+          sm.strip[r0 + rr][c][xx] = (uint8_t)clip8(acc);
         }
       } else {
-        for (int rr = rp; rr < rows; rr += kRowPar) {
-          const uint8_t* g = crop + (int64_t)(rmin + rr) * pitch + x_lo * 3;
+        for (int rr = rp; rr < nr; rr += kRowPar) {
+          const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
           const uint8_t* p = sm.stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + cofs;
           int acc = 1 << (kPrec - 1);
-          for (int x = 0; x < xcnt; ++x) acc += (int)p[x * 3] * kx_big[x];
-          sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
+#pragma unroll 4
+          for (int x = 0; x < xcnt; ++x) acc += (int)p[x * 3] * sm.xkT[x][xx];
+          sm.strip[r0 + rr][c][xx] = (uint8_t)clip8(acc);
         }
-      }
-    } else if (xcnt <= 4) {
-      // <= 4 taps (every up-scale and down-scales to 1.5x): 4 rows x 4 taps of byte loads in flight
-      for (int rr = rp; rr < rows; rr += 4 * kRowPar) {
-        int px[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r2 = min(rr + u * kRowPar, rows - 1);
-          const uint8_t* p = col + (int64_t)(rmin + r2) * pitch;
-#pragma unroll
-          for (int x = 0; x < 4; ++x) px[u][x] = (x < xcnt) ? (int)__ldg(p + x * 3) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r2 = rr + u * kRowPar;
-          int acc = 1 << (kPrec - 1);
-#pragma unroll
-          for (int x = 0; x < 4; ++x) acc += px[u][x] * kx[x];
-          if (r2 < rows) sm.strip[r2][c][xx] = (uint8_t)clip8(acc);
-        }
-      }
-    } else if (fast_x) {
-#pragma unroll 2
-      for (int rr = rp; rr < rows; rr += kRowPar) {
-        const uint8_t* p = col + (int64_t)(rmin + rr) * pitch;
-        int acc = 1 << (kPrec - 1);
-#pragma unroll
-        for (int x = 0; x < kFastTaps; ++x)
-          if (x < xcnt) acc += (int)__ldg(p + x * 3) * kx[x];
-        sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
-      }
-    } else {
-      for (int rr = rp; rr < rows; rr += kRowPar) {
-        const uint8_t* p = col + (int64_t)(rmin + rr) * pitch;
-        int acc = 1 << (kPrec - 1);
-        for (int x = 0; x < xcnt; ++x) acc += (int)__ldg(p + x * 3) * kx_big[x];
-        sm.strip[rr][c][xx] = (uint8_t)clip8(acc);
       }
     }
     __syncthreads();
@@ -258,7 +229,7 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
     __syncthreads();
     t0 = t1;
   }
-  if (tid == 0) *valid_out = 1;
+  if (tid == 0 && part == 0 && nparts == 1) *valid_out = 1;
 }
 
 // ROI list form: boxes (N,4) float + batch_idx (N).
@@ -275,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_kernel(const uint8_t* __restr
   // int() truncation of the float box (detect.py:581)
   roi_body(frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
            __float2int_rz(boxes[r * 4 + 1]), __float2int_rz(boxes[r * 4 + 2]), __float2int_rz(boxes[r * 4 + 3]), pad,
-           dst + (int64_t)r * 3 * kS * kS, valid + r, sm);
+           dst + (int64_t)r * 3 * kS * kS, valid + r, sm, 0, 1);
 }
 
 // Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
@@ -344,7 +315,55 @@ __global__ void __launch_bounds__(kThreads, 2) roi_det_kernel(const uint8_t* __r
   const float* row = det + ((int64_t)b * max_det + i) * 6;
   if (tid == 0) { roi_batch[g] = b; roi_det[g] = i; }
   roi_body(frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
-           __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm);
+           __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm, 0, 1);
+}
+
+// Second launch of K5: the ROIs the first launch marked valid == 2 (crop area > kBigArea).  CTA (j, part)
+// grid-strides over the deferred list (j-th marked slot, found by a block scan over valid[]) and produces
+// kS/kBigParts output rows of it.  When nothing was deferred every CTA exits after the scan.
+__global__ void __launch_bounds__(kThreads, 2) roi_big_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi,
+                                                              int B, int H, int W, int64_t pitch, int64_t bstride,
+                                                              const float* __restrict__ boxes,      // list form
+                                                              const int* __restrict__ batch_idx,    // list form / roi_batch
+                                                              const float* __restrict__ det,        // detection form
+                                                              const int* __restrict__ roi_det, int max_det,
+                                                              const int* __restrict__ count_ptr, int N, int pad,
+                                                              float* __restrict__ dst, int* __restrict__ valid) {
+  extern __shared__ __align__(16) uint8_t roi_smem[];
+  RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
+  __shared__ int wsum[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = count_ptr ? min(*count_ptr, N) : N;
+  for (int j = blockIdx.x;; j += gridDim.x) {
+    // locate the j-th deferred slot
+    if (tid == 0) sm.sel[0] = -1;
+    int carry = 0;
+    for (int base = 0; base < n && carry <= j; base += kThreads) {
+      const int g = base + tid;
+      const int v = (g < n && valid[g] == 2) ? 1 : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) wsum[wid] = __popc(bal);
+      __syncthreads();
+      int wbase = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) { if (w < wid) wbase += wsum[w]; tot += wsum[w]; }
+      if (v && carry + wbase + __popc(bal & ((1u << lane) - 1u)) == j) sm.sel[0] = g;
+      carry += tot;
+      __syncthreads();
+    }
+    __syncthreads();
+    const int g = sm.sel[0];
+    __syncthreads();
+    if (g < 0) return;                      // fewer than j+1 deferred ROIs: done (uniform)
+    int bi;
+    const float* bx;
+    if (det != nullptr) { bi = batch_idx[g]; bx = det + ((int64_t)bi * max_det + roi_det[g]) * 6; }
+    else { bi = batch_idx[g]; bx = boxes + (int64_t)g * 4; }
+    roi_body(frames, buf_hi, B, H, W, pitch, bstride, bi, __float2int_rz(bx[0]), __float2int_rz(bx[1]),
+             __float2int_rz(bx[2]), __float2int_rz(bx[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm,
+             blockIdx.y, kBigParts);
+    __syncthreads();
+  }
 }
 
 // ---- ROI selection: detections of the allowed classes -> dense list, image-major, order kept ----
@@ -443,6 +462,10 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
   const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
   roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
                                                            batch_idx, roi_count, pad, dst, valid);
+  e = cudaFuncSetAttribute(roi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  roi_big_kernel<<<dim3(kBigCtas, kBigParts), kThreads, smem, (cudaStream_t)stream>>>(
+      frames, buf_hi, B, H, W, pitch, batch_stride, boxes, batch_idx, nullptr, nullptr, 0, roi_count, N, pad, dst, valid);
   return b200_launch_status();
 }
 
@@ -463,6 +486,11 @@ extern "C" int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H,
   roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, det,
                                                                     det_count, roi_cnt, max_det, class_mask, nc, pad,
                                                                     dst, roi_batch, roi_det, valid, roi_total, roi_cap);
+  e = cudaFuncSetAttribute(roi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  roi_big_kernel<<<dim3(kBigCtas, kBigParts), kThreads, smem, (cudaStream_t)stream>>>(
+      frames, buf_hi, B, H, W, pitch, batch_stride, nullptr, roi_batch, det, roi_det, max_det, roi_total, roi_cap, pad, dst,
+      valid);
   return b200_launch_status();
 }
 

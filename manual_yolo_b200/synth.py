@@ -114,6 +114,7 @@ def synth_head_from_labels(B, nc=64, in_hw=(640, 640), src_hw=(1200, 1920), seed
         img = pool[pick[b]]
         rows = labels["boxes"][labels["box_img"] == img]
         gt = []
+        taken = set()          # one object per anchor, as a trained head produces (no class/box mix-ups)
         for cls_id, cx, cy, bw, bh in rows:
             cls_id = int(cls_id) % nc
             x1 = (cx - bw / 2) * src_hw[1] * r + left
@@ -136,7 +137,9 @@ def synth_head_from_labels(B, nc=64, in_hw=(640, 640), src_hw=(1200, 1920), seed
             mx, my = (x1 + x2) / 2 / s - 0.5, (y1 + y2) / 2 / s - 0.5
             cells.sort(key=lambda c: (c[0] - mx) ** 2 + (c[1] - my) ** 2)
             k = 1 + int(torch.randint(0, max_anchors_per_box, (1,), generator=g))
+            cells = [cc for cc in cells if (li, cc[0], cc[1]) not in taken]
             for ax, ay in cells[:k]:
+                taken.add((li, ax, ay))
                 a = int(offs[li]) + ay * w + ax
                 px, py = (ax + 0.5) * s, (ay + 0.5) * s
                 dist = torch.tensor([px - x1, py - y1, x2 - px, y2 - py], dtype=torch.float32) / s
@@ -145,6 +148,15 @@ def synth_head_from_labels(B, nc=64, in_hw=(640, 640), src_hw=(1200, 1920), seed
                 head[b, :4 * REG_MAX, a] = (logits * 1.0 + 0.05 * torch.randn((4, REG_MAX), generator=g)).reshape(-1)
                 head[b, 4 * REG_MAX + cls_id, a] = 0.5 + 3.5 * float(torch.rand((1,), generator=g))
         gts.append(np.asarray(gt, np.float32).reshape(-1, 5))
+        # a trained head does not fire on background: keep the N(-6,1) class clutter of unassigned anchors
+        # below the threshold (logit(conf) - 1), so every candidate belongs to a labelled object and the
+        # ROI sizes follow the dataset's rank-box statistics instead of random clutter boxes
+        bg = torch.ones(A, dtype=torch.bool)
+        if taken:
+            bg[torch.tensor([int(offs[l]) + y * lv[l][1] + x for (l, x, y) in taken])] = False
+        ceil_logit = float(np.log(conf_thres / (1.0 - conf_thres))) - 1.0 if 0.0 < conf_thres < 1.0 else -2.0
+        cl = head[b, 4 * REG_MAX:, :]
+        cl[:, bg] = cl[:, bg].clamp(max=ceil_logit)
     if guard_ulp:
         guard_band(head, nc, conf_thres, guard_ulp)
     return head, gts

@@ -62,7 +62,7 @@ def test_synthetic_rois_vs_pil_oracle(cuda_dev):
     worst, exact = 0.0, 0
     for i in range(N):
         crop = oboxes.safe_crop_ref(frames[bidx[i]].numpy(), *[int(v) for v in boxes[i]], pad=6)
-        assert crop is not None and valid[i] == 1
+        assert crop is not None and valid[i] == (2 if crop.shape[0] * crop.shape[1] > 160 * 160 else 1)
         ref = oroi.classify_preprocess_ref(crop)
         d = (out[i] - ref).abs().max().item()
         worst, exact = max(worst, d), exact + (d == 0.0)
@@ -87,8 +87,29 @@ def test_invalid_border_and_large_rois(cuda_dev):
         if crop is None:
             assert valid[i] == 0 and float(out[i].abs().max()) == 0.0
         else:
-            assert valid[i] == 1
+            assert valid[i] == (2 if crop.shape[0] * crop.shape[1] > 160 * 160 else 1)   # 2 = large-ROI launch
             assert torch.equal(out[i], oroi.classify_preprocess_ref(crop)), i
+
+
+def test_large_rois_split_launch(cuda_dev):
+    """Crops far larger than a rank card (strong antialias, up to the whole frame) go through the split
+    large-ROI launch: still bit-exact against PIL, and more of them than the launch width."""
+    frames = synth.synth_frames(2, 700, 900, seed=9)
+    g = torch.Generator().manual_seed(4)
+    N = 40
+    x1 = torch.rand(N, generator=g) * 300
+    y1 = torch.rand(N, generator=g) * 200
+    w = 170 + torch.rand(N, generator=g) * 420
+    h = 170 + torch.rand(N, generator=g) * 320
+    boxes = torch.stack((x1, y1, x1 + w, y1 + h), 1)
+    boxes[0] = torch.tensor([0., 0., 900., 700.])
+    bidx = torch.randint(0, 2, (N,), generator=g, dtype=torch.int32)
+    out, valid = m.crop_resize_rois(frames.to(cuda_dev), boxes.to(cuda_dev), bidx.to(cuda_dev), pad=6)
+    out, valid = out.cpu(), valid.cpu().tolist()
+    assert valid == [2] * N
+    for i in range(N):
+        crop = oboxes.safe_crop_ref(frames[bidx[i]].numpy(), *[int(v) for v in boxes[i]], pad=6)
+        assert torch.equal(out[i], oroi.classify_preprocess_ref(crop)), i
 
 
 def test_select_rois_order_and_count(cuda_dev):
