@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int kChunk = 64;
-constexpr int kSmemBoxesMax = 12288;
+constexpr int kSmemBoxesMax = 10240;   // (16 + 1 + 4) B per box + keep list <= 227 KB
 
 __device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_a, const float4 b, const double thr) {
   const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
@@ -35,6 +35,22 @@ __device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
   return (double)ovr > thr;
 }
+
+// Exact shortcut of the class-offset trick: when both raw boxes lie inside [-max_wh/2, max_wh/2) on every
+// coordinate, boxes of different classes occupy disjoint offset ranges [(c-1/2)*max_wh, (c+1/2)*max_wh]
+// (end points exact in fp32, rounding is monotone), so inter == 0 and the pair can never suppress.  meta = class id for such boxes, -1 otherwise (agnostic mode, out-of-range or
+// non-integral class, NaN): pairs involving a -1 always take the full IoU test.
+__device__ __forceinline__ int box_meta(const float* row, float max_wh, int agnostic) {
+  if (agnostic) return -1;
+  const float c = row[5];
+  const float hw = 0.5f * max_wh;
+  const bool inb = row[0] >= -hw && row[0] < hw && row[1] >= -hw && row[1] < hw && row[2] >= -hw && row[2] < hw &&
+                   row[3] >= -hw && row[3] < hw;
+  // (c +- 1/2)*max_wh must be exact in fp32: integral class, even integral max_wh, products < 2^24
+  if (!inb || !(c >= 0.f) || c != floorf(c) || hw != floorf(hw) || (c + 1.f) * max_wh >= 16777216.f) return -1;
+  return (int)c;
+}
+__device__ __forceinline__ bool may_overlap(int mi, int mj) { return mi == mj || (mi | mj) < 0; }
 
 template <int NT>
 __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
@@ -49,11 +65,14 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
   float4* sbox = reinterpret_cast<float4*>(smem_raw);
   uint8_t* removed = reinterpret_cast<uint8_t*>(sbox + smem_boxes);   // [smem_boxes or n]
   int* keep = reinterpret_cast<int*>(removed + ((smem_boxes + 15) & ~15));  // [max_det]
+  int* smeta = keep + ((max_det + 3) & ~3);                                 // [smem_boxes] class id, or -1
   __shared__ unsigned long long mask[kChunk];
   __shared__ unsigned rem_bits[2];
   __shared__ unsigned long long kept_bits_s;
   __shared__ int kcount_s;
   __shared__ int roi_s;
+  __shared__ unsigned long long cmask[128];   // per chunk: kept boxes by (class & 127); see phase (C)
+  __shared__ unsigned long long always_s;      // kept boxes that must be tested against every class (meta -1)
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = min(min(min(cand_count[b], cap), max_nms), B200YOLO_MAX_SORT);
@@ -65,6 +84,8 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
   }
   float4* box = sbox;
   uint8_t* rem = removed;
+  int* meta = smeta;
+  const bool use_meta = n <= smem_boxes;   // oversize images (workspace path) always run the full IoU test
   if (n > smem_boxes) {  // oversize image: boxes + flags in the workspace (L2-resident)
     box = ws + (int64_t)b * (cap + (cap + 15) / 16);
     rem = reinterpret_cast<uint8_t*>(box + cap);
@@ -74,6 +95,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
     const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
     box[r] = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
     rem[r] = 0;
+    if (use_meta) meta[r] = box_meta(row, max_wh, agnostic);
   }
   if (tid == 0) { kcount_s = 0; roi_s = 0; }
   __syncthreads();
@@ -90,7 +112,9 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = jg * 4 + u;
-          if (j > i && j < m && iou_suppresses(bi, ai, box[s + j], thr)) nib |= 1u << u;
+          if (j > i && j < m && (!use_meta || may_overlap(meta[s + i], meta[s + j])) &&
+              iou_suppresses(bi, ai, box[s + j], thr))
+            nib |= 1u << u;
         }
       }
       unsigned lo = jg < 8 ? nib << (jg * 4) : 0u;
@@ -128,15 +152,35 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
     const int kc = kcount_s;
     if (kc >= max_det) break;
     // ---- (C) apply this chunk's kept boxes to all later boxes ----
+    // Class-aware shortcut (exact, see box_meta): a later box only needs the kept boxes of its own class.
+    // The chunk's kept boxes are bucketed by (class & 127) into 64-bit masks, so a thread visits 0-2
+    // kept boxes per later box instead of up to 64.
     const unsigned long long kept = kept_bits_s;
     if (kept) {
+      if (use_meta) {
+        if (tid < 128) cmask[tid] = 0ull;
+        if (tid == 128) always_s = 0ull;
+        __syncthreads();
+        if (tid < kChunk && ((kept >> tid) & 1ull)) {
+          const int mi = meta[s + tid];
+          if (mi < 0) atomicOr(&always_s, 1ull << tid);
+          else atomicOr(&cmask[mi & 127], 1ull << tid);
+        }
+        __syncthreads();
+      }
       for (int j = s + kChunk + tid; j < n; j += NT) {
         if (rem[j]) continue;
         const float4 bj = box[j];
         unsigned long long kb = kept;
+        int mj = -1;
+        if (use_meta) {
+          mj = meta[j];
+          if (mj >= 0) kb = cmask[mj & 127] | always_s;
+        }
         while (kb) {
           const int i = __ffsll((long long)kb) - 1;
           kb &= kb - 1;
+          if (use_meta && !may_overlap(meta[s + i], mj)) continue;   // bucket collision (class & 127)
           const float4 bi = box[s + i];
           const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
           if (iou_suppresses(bi, ai, bj, thr)) { rem[j] = 1; break; }
@@ -201,7 +245,8 @@ extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int
     B200_REQUIRE(workspace_bytes >= (size_t)B * ((size_t)cap + (cap + 15) / 16) * 16, B200YOLO_ERR_WORKSPACE);
   }
   const int smem_boxes = cap < kSmemBoxesMax ? cap : kSmemBoxesMax;
-  const size_t smem = (size_t)smem_boxes * 16 + (((size_t)smem_boxes + 15) & ~(size_t)15) + (size_t)max_det * 4;
+  const size_t smem = (size_t)smem_boxes * 16 + (((size_t)smem_boxes + 15) & ~(size_t)15) +
+                      (((size_t)max_det + 3) & ~(size_t)3) * 4 + (size_t)smem_boxes * 4;
   cudaStream_t s = (cudaStream_t)stream;
   if (cap <= 1024) {
     constexpr int NT = 256;

@@ -39,6 +39,22 @@ __device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_
   return (double)ovr > thr;
 }
 
+// Exact shortcut of the class-offset trick: when both raw boxes lie inside [-max_wh/2, max_wh/2) on every
+// coordinate, boxes of different classes occupy disjoint offset ranges [(c-1/2)*max_wh, (c+1/2)*max_wh]
+// (end points exact in fp32, rounding is monotone), so inter == 0 and the pair can never suppress.  meta = class id for such boxes, -1 otherwise (agnostic mode, out-of-range or
+// non-integral class, NaN): pairs involving a -1 always take the full IoU test.
+__device__ __forceinline__ int box_meta(const float* row, float max_wh, int agnostic) {
+  if (agnostic) return -1;
+  const float c = row[5];
+  const float hw = 0.5f * max_wh;
+  const bool inb = row[0] >= -hw && row[0] < hw && row[1] >= -hw && row[1] < hw && row[2] >= -hw && row[2] < hw &&
+                   row[3] >= -hw && row[3] < hw;
+  // (c +- 1/2)*max_wh must be exact in fp32: integral class, even integral max_wh, products < 2^24
+  if (!inb || !(c >= 0.f) || c != floorf(c) || hw != floorf(hw) || (c + 1.f) * max_wh >= 16777216.f) return -1;
+  return (int)c;
+}
+__device__ __forceinline__ bool may_overlap(int mi, int mj) { return mi == mj || (mi | mj) < 0; }
+
 struct Smem {
   float rows[kCapMax][6];            // x1,y1,x2,y2,score,class (slot order)
   int anchor[kCapMax];
@@ -49,6 +65,7 @@ struct Smem {
   uint32_t hist[W * 256];
   int order[kCapMax];
   uint8_t rem[kCapMax];
+  int meta[kCapMax];                 // class id of the sorted box, or -1 (always run the full IoU test)
   unsigned long long mask[kChunk];
   uint32_t warp_tot[32];
   unsigned rem_bits[2];
@@ -211,6 +228,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
     const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
     sm.u.box[r] = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
     sm.rem[r] = 0;
+    sm.meta[r] = box_meta(row, max_wh, agnostic);
   }
   __syncthreads();
 
@@ -227,7 +245,8 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = jg * 4 + u;
-          if (j > i && j < m && iou_suppresses(bi, ai, box[s + j], thr)) nib |= 1u << u;
+          if (j > i && j < m && may_overlap(sm.meta[s + i], sm.meta[s + j]) && iou_suppresses(bi, ai, box[s + j], thr))
+            nib |= 1u << u;
         }
       }
       unsigned lo = jg < 8 ? nib << (jg * 4) : 0u;
@@ -267,10 +286,12 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
       for (int j = s + kChunk + tid; j < n_nms; j += NT) {
         if (sm.rem[j]) continue;
         const float4 bj = box[j];
+        const int mj = sm.meta[j];
         unsigned long long kb = kept;
         while (kb) {
           const int i = __ffsll((long long)kb) - 1;
           kb &= kb - 1;
+          if (!may_overlap(sm.meta[s + i], mj)) continue;
           const float4 bi = box[s + i];
           const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
           if (iou_suppresses(bi, ai, bj, thr)) { sm.rem[j] = 1; break; }
