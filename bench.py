@@ -310,7 +310,7 @@ def run_ours(args, rank, world, local):
         if name in bytes_per_launch:
             kernels[name]["algo_GBps"] = bytes_per_launch[name] / (statistics.mean(v) / 1e3) / 1e9
             kernels[name]["frac_of_measured_peak"] = kernels[name]["algo_GBps"] / peak
-    pipeline_bytes_frame = k1_bytes_frame + (64 + NC) * pipe.A * 4 + 10_000 + 4 * 60_000
+    pipeline_bytes_frame = k1_bytes_frame + (64 + NC) * pipe.A * 4 + 10_000 + 4 * 60_000   # 11.77 MB
     # ---- CPU baseline (oracle port) on a bounded sample of the same workload ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -5,15 +5,14 @@
 // ops.non_max_suppression (amax > conf, xywh2xyxy, cls.max, conf filter, classes filter) -- reference
 // entry detect.py:541 / yolo.py:361 / pipe.py:179.  Restated in oracle/head.py + oracle/nms.py.
 //
-// A CTA of 8 warps covers 64 consecutive anchors: two groups of 4 warps, each group owning 32 anchors
-// (lane = anchor, so every channel load is one coalesced 128-byte line).  Within a group the channel
-// axis is split four ways: warp q reduces class channels [q*nc/4, (q+1)*nc/4) -- all of a thread's loads
-// are independent and issued in ONE round (16 in flight for nc=64) -- and the partial (max, argmax)
-// pairs are merged through shared memory in class order (first-maximum semantics of cls.max(1)).
-// Work is lazy: only if some anchor of the CTA beats conf_thres (about 1% of anchors at conf 0.25, all of
-// them at conf 0.001) do the four warps of a group decode the four box sides (warp q = side q: 16 DFL
-// bins, softmax expectation), again one load round.  Survivors are compacted with a warp ballot and one
-// atomicAdd per group on the per-image counter.
+// Two kernels make up the fast path (see the block comment above decode_vec_kernel):
+//   decode_vec_kernel  streams the class channels with 128-bit loads (4 anchors per lane, channel
+//                      quarters per warp pair), thresholds the best sigmoid and compacts the survivors;
+//   box_decode_kernel  decodes the 64 DFL channels of the survivors only (4 lanes per box, lane = side).
+// Work is lazy: about 1% of the anchors survive conf 0.25, so the box channels of the other 99% are never
+// read.  decode_filter_kernel (first in this file) is the scalar fallback for shapes that are not
+// 16-byte aligned: 8 warps cover 64 anchors, lane = anchor, warp q reduces channel quarter q and, for the
+// survivors, decodes box side q.
 // HBM-bound: algorithmic bytes per frame = (64+nc)*A*4 read + 28 B per survivor written.
 // Compiled with -fmad=false: every add/mul below rounds separately, as the torch CPU ops do.
 
@@ -24,8 +23,6 @@ namespace {
 constexpr int kThreads = 256;
 using b200::kReg;
 using b200::Levels;
-
-
 
 __device__ __forceinline__ bool class_allowed(const uint32_t* mask, int c) {
   return mask == nullptr || ((mask[c >> 5] >> (c & 31)) & 1u);
