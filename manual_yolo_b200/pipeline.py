@@ -21,7 +21,6 @@ from . import api, geometry
 
 RANK_CLASS_IDS = (6, 11, 16, 21, 26, 37, 43)  # *_rank classes, roadmap1.v3i.yolov8/data.yaml:6
 FUSED_CAP_MAX = 1024                           # b200yolo_postprocess_small envelope
-GPU_LAUNCHES_PER_STEP = 6                      # letterbox, class filter, box decode, sort_topk, nms, roi_from_detections
 
 
 @dataclass
@@ -207,8 +206,9 @@ class Pipeline:
         return h_rows, h_count, h_roi
 
     def launches_per_step(self):
-        """Kernels of this package launched per step (class filter [+ box decode, sort, nms | fused], letterbox, roi)."""
-        return 4 if self.fused else 6
+        """Kernels of this package launched per step: letterbox, class filter, [fused post-processing | box
+        decode, sort, nms], ROI crops, large-ROI pass."""
+        return 5 if self.fused else 7
 
     def check_overflow(self):
         """Raise if any image of the last step had more candidates than ``cap`` (one D2H of the counts).
@@ -240,8 +240,10 @@ class HostRunner:
     host memory (copy stream), runs the device path (compute stream) and reads the detections back.
     Two staging sets let step i+1's H2D overlap step i's kernels."""
 
-    def __init__(self, pipe: Pipeline, depth=2):
-        self.pipe, self.depth = pipe, depth
+    def __init__(self, pipe: Pipeline, depth=2, head_resident=None):
+        """``head_resident``: a device head tensor to use every step instead of copying one from the host
+        (the deployment case: the Detect head is produced on the device by the backbone)."""
+        self.pipe, self.depth, self.head_resident = pipe, depth, head_resident
         self.staging = [pipe.make_staging() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=pipe.device)
         self.ready = [torch.cuda.Event() for _ in range(depth)]
@@ -257,10 +259,11 @@ class HostRunner:
             if self.step >= self.depth:
                 self.copy_stream.wait_event(self.free[s])
             d_frames.copy_(frames_host, non_blocking=True)
-            d_head.copy_(head_host, non_blocking=True)
+            if self.head_resident is None:
+                d_head.copy_(head_host, non_blocking=True)
             self.ready[s].record(self.copy_stream)
         compute.wait_event(self.ready[s])
-        res = self.pipe(d_frames, d_head)
+        res = self.pipe(d_frames, d_head if self.head_resident is None else self.head_resident)
         h_rows.copy_(res.det.rows, non_blocking=True)
         h_count.copy_(res.det.count, non_blocking=True)
         h_roi.copy_(res.roi_count, non_blocking=True)

@@ -134,3 +134,21 @@ def test_scale_boxes_bit_exact(cuda_dev):
         exp = ref[bi].clone()
         exp[:, :4] = oboxes.scale_boxes_ref((640, 640), exp[:, :4], (1200, 1920))
         assert torch.equal(det.rows[bi, :int(det.count[bi])].cpu(), exp)
+
+
+def test_oversize_images_use_workspace_paths(cuda_dev):
+    """pipe.py runs imgsz=1280 (928x1280 rect -> 24 360 anchors): with a low threshold an image has more
+    candidates than fit the shared-memory sort/NMS paths (12 288 keys / 10 240 boxes), so the L2-resident
+    workspace paths run.  Same bit-exact bar."""
+    g = torch.Generator().manual_seed(11)
+    A, nc = 24360, 8
+    pred = torch.zeros((2, 4 + nc, A))
+    pred[:, 0] = torch.rand((2, A), generator=g) * 1200
+    pred[:, 1] = torch.rand((2, A), generator=g) * 900
+    pred[:, 2] = torch.rand((2, A), generator=g) * 60 + 4
+    pred[:, 3] = torch.rand((2, A), generator=g) * 60 + 4
+    pred[:, 4:] = torch.rand((2, nc, A), generator=g) * 0.5
+    pred[1, 4:, 15000:] = 0.0                                   # image 1: 15 000 candidates, image 0: all 24 360
+    kept = _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.6, max_det=500)
+    assert kept == 1000
+    _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.45, max_det=300, max_nms=13000)
