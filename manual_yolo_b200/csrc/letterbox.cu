@@ -71,7 +71,7 @@ template <>
 __device__ __forceinline__ uint8_t lb_cast<uint8_t>(const float*, int v) { return (uint8_t)v; }
 
 constexpr int kRows = 8;     // output rows per CTA
-constexpr int kStages = 2;
+constexpr int kStages = 2;   // ring slots: row r+1 is in flight while row r is blended (3 and 4 slots measured: no gain)
 
 struct RowInfo { int r0, r1, b0, b1; };   // b0 < 0 marks a padding row
 
@@ -213,12 +213,15 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
   OutCursor<OutT> cur;
   if (have) cur.init(p, b, oy0, ox0, npx);
   const OutT padv = lb_cast<OutT>(lut, p.pad_value);
-  int uses0 = 0, uses1 = 0;                  // completed phases per ring slot (only interior rows arm it)
-  prefetch(0, 0);
+  unsigned uses = 0;                         // bit s = parity of completed phases of ring slot s (interior rows only)
+#pragma unroll
+  for (int r = 0; r < kStages - 1; ++r)
+    if (r < nrows) prefetch(r, r);
   for (int r = 0; r < nrows; ++r) {
-    const int s = r & 1;
+    const int s = r % kStages;
     const RowInfo ri = rows[r];
-    if (r + 1 < nrows) prefetch(r + 1, s ^ 1);       // slot s^1 was released by the barrier ending row r-1
+    // slot (r-1) % kStages was released by the barrier that ended row r-1: refill it with row r+kStages-1
+    if (r + kStages - 1 < nrows) prefetch(r + kStages - 1, (r + kStages - 1) % kStages);
     OutT v[4][3];
     if (ri.b0 < 0 || nbytes <= 0) {                  // CTA-uniform: padding row / chunk fully in the side padding
 #pragma unroll
@@ -228,8 +231,8 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
       continue;
     }
     if (p.bulk_ok) {
-      if (s == 0) { b200::mbar_wait(&bar[0], uses0 & 1); ++uses0; }
-      else { b200::mbar_wait(&bar[1], uses1 & 1); ++uses1; }
+      b200::mbar_wait(&bar[s], (uses >> s) & 1u);
+      uses ^= 1u << s;
     } else {
       __syncthreads();
     }

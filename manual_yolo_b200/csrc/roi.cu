@@ -157,7 +157,7 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
   // horizontal span of source columns the 64 surviving output columns reference
   const int x_lo = sm.xb[0][0];
   const int span_bytes = (sm.xb[kS - 1][0] + sm.xb[kS - 1][1] - x_lo) * 3;
-  const int row_words = (span_bytes + 3 + 3) / 4;            // any 4-byte phase fits
+  const int row_words = (span_bytes + 3 + 3) / 4 + 3;        // any 4-byte phase fits, + slack for the 4-tap reads
   const int row_stride = row_words * 4;
   const int stage_rows = kStageBytes / row_stride;            // rows of this ROI one stage fill can hold (>= 1)
   const int cofs = (xmin - x_lo) * 3 + c;
@@ -173,14 +173,26 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
     for (int r0 = 0; r0 < rows; r0 += stage_rows) {
       const int nr = min(stage_rows, rows - r0);
       if (r0 > 0) __syncthreads();                            // previous chunk fully consumed
-      for (int e = tid; e < nr * row_words; e += kThreads) {
-        const int rr = e / row_words, wd = e - rr * row_words;
-        const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
-        const uint8_t* ga = g - (reinterpret_cast<uintptr_t>(g) & 3) + wd * 4;
-        reinterpret_cast<uint32_t*>(sm.stage + rr * row_stride)[wd] = load_word_guarded(ga, frames, buf_hi);
+      {   // warp per row, lanes stride over the row's words (no integer division per element)
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int rr = wid; rr < nr; rr += kThreads / 32) {
+          const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
+          const uint8_t* ga = g - (reinterpret_cast<uintptr_t>(g) & 3);
+          uint32_t* srow = reinterpret_cast<uint32_t*>(sm.stage + rr * row_stride);
+          for (int wd = lane; wd < row_words; wd += 32) srow[wd] = load_word_guarded(ga + wd * 4, frames, buf_hi);
+        }
       }
       __syncthreads();
-      if (fast_x) {
+      if (xcnt <= 4) {
+        // <= 4 taps: every up-scale and down-scales to 1.5x (the rank-card case)
+        for (int rr = rp; rr < nr; rr += kRowPar) {
+          const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
+          const uint8_t* p = sm.stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + cofs;
+          // taps beyond xcnt have weight 0; their bytes are inside the staged row (+ slack words)
+          const int acc = (1 << (kPrec - 1)) + (int)p[0] * kx[0] + (int)p[3] * kx[1] + (int)p[6] * kx[2] + (int)p[9] * kx[3];
+          sm.strip[r0 + rr][c][xx] = (uint8_t)clip8(acc);
+        }
+      } else if (fast_x) {
         for (int rr = rp; rr < nr; rr += kRowPar) {
           const uint8_t* g = crop + (int64_t)(rmin + r0 + rr) * pitch + x_lo * 3;
           const uint8_t* p = sm.stage + rr * row_stride + (reinterpret_cast<uintptr_t>(g) & 3) + cofs;
