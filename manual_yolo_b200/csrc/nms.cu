@@ -18,39 +18,19 @@
 // (ffs over the alive bits), (C) the chunk's kept boxes are applied to every later box in parallel.
 // Total IoU work <= kept * n instead of n^2/2.  Compiled with -fmad=false.
 
-#include "common.cuh"
+#include "nms_common.cuh"
 
 namespace {
+
+using b200::box_meta;
+using b200::iou_suppresses;
+using b200::may_overlap;
+using b200::scale_clip;
 
 constexpr int kChunk = 64;
 constexpr int kSmemBoxesMax = 10240;   // (16 + 1 + 4) B per box + keep list <= 227 KB
 
-__device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_a, const float4 b, const double thr) {
-  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-  const float inter = __fmul_rn(w, h);
-  if (!(inter > 0.f)) return false;  // ovr is 0, -0 or NaN: never > thr (thr >= 0)
-  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-  return (double)ovr > thr;
-}
 
-// Exact shortcut of the class-offset trick: when both raw boxes lie inside [-max_wh/2, max_wh/2) on every
-// coordinate, boxes of different classes occupy disjoint offset ranges [(c-1/2)*max_wh, (c+1/2)*max_wh]
-// (end points exact in fp32, rounding is monotone), so inter == 0 and the pair can never suppress.  meta = class id for such boxes, -1 otherwise (agnostic mode, out-of-range or
-// non-integral class, NaN): pairs involving a -1 always take the full IoU test.
-__device__ __forceinline__ int box_meta(const float* row, float max_wh, int agnostic) {
-  if (agnostic) return -1;
-  const float c = row[5];
-  const float hw = 0.5f * max_wh;
-  const bool inb = row[0] >= -hw && row[0] < hw && row[1] >= -hw && row[1] < hw && row[2] >= -hw && row[2] < hw &&
-                   row[3] >= -hw && row[3] < hw;
-  // (c +- 1/2)*max_wh must be exact in fp32: integral class, even integral max_wh, products < 2^24
-  if (!inb || !(c >= 0.f) || c != floorf(c) || hw != floorf(hw) || (c + 1.f) * max_wh >= 16777216.f) return -1;
-  return (int)c;
-}
-__device__ __forceinline__ bool may_overlap(int mi, int mj) { return mi == mj || (mi | mj) < 0; }
 
 template <int NT>
 __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
@@ -199,10 +179,8 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
     const float* row = crow + (int64_t)slot * 6;
     float x1 = row[0], y1 = row[1], x2 = row[2], y2 = row[3];
     if (scale) {
-      x1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x1, padx), gain), 0.f), w0);
-      y1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y1, pady), gain), 0.f), h0);
-      x2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x2, padx), gain), 0.f), w0);
-      y2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y2, pady), gain), 0.f), h0);
+      x1 = scale_clip(x1, padx, gain, w0); y1 = scale_clip(y1, pady, gain, h0);
+      x2 = scale_clip(x2, padx, gain, w0); y2 = scale_clip(y2, pady, gain, h0);
     }
     float* o = out + ((int64_t)b * max_det + r) * 6;
     o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = row[4]; o[5] = row[5];
@@ -221,10 +199,8 @@ __global__ void scale_boxes_kernel(float* boxes, int n, int row_stride, float ga
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float* r = boxes + (int64_t)i * row_stride;
-  r[0] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[0], padx), gain), 0.f), w0);
-  r[1] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[1], pady), gain), 0.f), h0);
-  r[2] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[2], padx), gain), 0.f), w0);
-  r[3] = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[3], pady), gain), 0.f), h0);
+  r[0] = scale_clip(r[0], padx, gain, w0); r[1] = scale_clip(r[1], pady, gain, h0);
+  r[2] = scale_clip(r[2], padx, gain, w0); r[3] = scale_clip(r[3], pady, gain, h0);
 }
 
 }  // namespace

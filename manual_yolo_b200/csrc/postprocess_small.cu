@@ -13,47 +13,24 @@
 // ops.scale_boxes + clip_boxes.  Compiled with -fmad=false.
 
 #include "levels.cuh"
+#include "nms_common.cuh"
 
 namespace {
 
 using b200::Levels;
+using b200::box_meta;
+using b200::iou_suppresses;
+using b200::make_key;
+using b200::may_overlap;
+using b200::scale_clip;
 constexpr int NT = 1024;    // 32 warps per image: every phase below is one pass at n ~ 100
 constexpr int W = NT / 32;
 constexpr int kCapMax = 1024;
 constexpr int kEnumMax = 512;
 constexpr int kChunk = 64;
 
-__device__ __forceinline__ uint64_t make_key(float score, int anchor, int slot) {
-  const uint32_t sb = ~__float_as_uint(score);
-  return ((uint64_t)sb << 32) | ((uint64_t)(uint32_t)(anchor & 0xffff) << 16) | (uint32_t)(slot & 0xffff);
-}
 
-__device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_a, const float4 b, const double thr) {
-  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-  const float inter = __fmul_rn(w, h);
-  if (!(inter > 0.f)) return false;  // ovr is 0, -0 or NaN: never > thr (thr >= 0)
-  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-  return (double)ovr > thr;
-}
 
-// Exact shortcut of the class-offset trick: when both raw boxes lie inside [-max_wh/2, max_wh/2) on every
-// coordinate, boxes of different classes occupy disjoint offset ranges [(c-1/2)*max_wh, (c+1/2)*max_wh]
-// (end points exact in fp32, rounding is monotone), so inter == 0 and the pair can never suppress.  meta = class id for such boxes, -1 otherwise (agnostic mode, out-of-range or
-// non-integral class, NaN): pairs involving a -1 always take the full IoU test.
-__device__ __forceinline__ int box_meta(const float* row, float max_wh, int agnostic) {
-  if (agnostic) return -1;
-  const float c = row[5];
-  const float hw = 0.5f * max_wh;
-  const bool inb = row[0] >= -hw && row[0] < hw && row[1] >= -hw && row[1] < hw && row[2] >= -hw && row[2] < hw &&
-                   row[3] >= -hw && row[3] < hw;
-  // (c +- 1/2)*max_wh must be exact in fp32: integral class, even integral max_wh, products < 2^24
-  if (!inb || !(c >= 0.f) || c != floorf(c) || hw != floorf(hw) || (c + 1.f) * max_wh >= 16777216.f) return -1;
-  return (int)c;
-}
-__device__ __forceinline__ bool may_overlap(int mi, int mj) { return mi == mj || (mi | mj) < 0; }
 
 struct Smem {
   float rows[kCapMax][6];            // x1,y1,x2,y2,score,class (slot order)
@@ -311,10 +288,8 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
     const float* row = sm.rows[slot];
     float x1 = row[0], y1 = row[1], x2 = row[2], y2 = row[3];
     if (scale) {
-      x1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x1, padx), gain), 0.f), w0);
-      y1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y1, pady), gain), 0.f), h0);
-      x2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x2, padx), gain), 0.f), w0);
-      y2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y2, pady), gain), 0.f), h0);
+      x1 = scale_clip(x1, padx, gain, w0); y1 = scale_clip(y1, pady, gain, h0);
+      x2 = scale_clip(x2, padx, gain, w0); y2 = scale_clip(y2, pady, gain, h0);
     }
     float2* o = reinterpret_cast<float2*>(out + ((int64_t)b * max_det + r) * 6);
     o[0] = make_float2(x1, y1); o[1] = make_float2(x2, y2); o[2] = make_float2(row[4], row[5]);

@@ -15,17 +15,15 @@
 //              32-key row); passes whose digit is uniform across the image are skipped.
 // Latency-bound: reported in microseconds, not GB/s.
 
-#include "common.cuh"
+#include "nms_common.cuh"
 
 namespace {
+
+using b200::make_key;
 
 constexpr int kEnumMax = 512;
 constexpr int kSmemKeysMax = 12288;  // 2 * 8 B * 12288 + 32 KB histograms = 224 KB
 
-__device__ __forceinline__ uint64_t make_key(float score, int anchor, int slot) {
-  const uint32_t sb = ~__float_as_uint(score);
-  return ((uint64_t)sb << 32) | ((uint64_t)(uint32_t)(anchor & 0xffff) << 16) | (uint32_t)(slot & 0xffff);
-}
 
 template <int NT>
 __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__ cand,
