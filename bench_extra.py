@@ -135,6 +135,30 @@ def calibration(dev):
     return out
 
 
+def cpu_threads(dev, n=16):
+    """The CPU oracle on the headline workload with all host threads and with one thread."""
+    import cv2
+    from bench import BATCH, CONF, IMGSZ, NC, SRC_HW, cpu_path_frames_per_s
+    frames = synth.synth_frames(n, *SRC_HW, seed=0).numpy()
+    lv = geometry.level_shapes(IMGSZ, IMGSZ)
+    head, _ = synth.synth_head_from_labels(n, NC, in_hw=(IMGSZ, IMGSZ), src_hw=SRC_HW, seed=0, conf_thres=CONF)
+    out = {}
+    fps, cores, dt = cpu_path_frames_per_s(frames, head, lv, (IMGSZ, IMGSZ), 2)
+    out["all_threads"] = {"frames_per_s": fps, "cores": cores, "seconds": dt}
+    torch.set_num_threads(1)
+    cv2.setNumThreads(1)
+    t0 = time.perf_counter()
+    from oracle import head as ohead, letterbox as olb, nms as onms
+    for _ in range(2):
+        olb.preprocess_ref(list(frames), (IMGSZ, IMGSZ))
+        onms.non_max_suppression_ref(ohead.detect_inference_ref(head, lv), CONF, 0.45)
+    out["one_thread"] = {"frames_per_s": 2 * n / (time.perf_counter() - t0), "cores": 1,
+                         "note": "letterbox + decode + NMS only (ROI stage excluded)"}
+    torch.set_num_threads(os.cpu_count())
+    cv2.setNumThreads(os.cpu_count())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_extra.json"))
@@ -142,7 +166,7 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     res = {"calibration": calibration(dev), "config3_nms_heavy": config3(dev, B=args.b3),
-           "config4_roi_4096": config4(dev), "config1_single_frame": config1(dev)}
+           "config4_roi_4096": config4(dev), "config1_single_frame": config1(dev), "cpu_oracle_threads": cpu_threads(dev)}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     print(json.dumps(res))

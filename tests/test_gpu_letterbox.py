@@ -80,3 +80,19 @@ def test_upscale_bit_exact(cuda_dev, hw, new):
     assert np.array_equal(got, ref)
     assert torch.equal(m.preprocess(torch.from_numpy(f).to(cuda_dev), new, auto=True).cpu(),
                        olb.preprocess_ref(list(f), new, auto=True))
+
+
+def test_letterbox_flags_scaleup_center_scalefill(cuda_dev):
+    """The remaining LetterBox.__call__ options (scaleup=False, center=False, scale_fill=True, stride 64)."""
+    def ul(img, new_shape, auto=False, scale_fill=False, scaleup=True, center=True, stride=32):
+        g = olb.letterbox_geometry(img.shape[:2], new_shape, auto, scale_fill, scaleup, center, stride)
+        out = img
+        if (img.shape[1], img.shape[0]) != (g["new_w"], g["new_h"]):
+            out = cv2.resize(img, (g["new_w"], g["new_h"]), interpolation=cv2.INTER_LINEAR)
+        return cv2.copyMakeBorder(out, g["top"], g["bottom"], g["left"], g["right"], cv2.BORDER_CONSTANT, value=(114,) * 3)
+    for hw, kw in [((300, 400), dict(scaleup=False)), ((900, 1600), dict(center=False)),
+                   ((900, 1600), dict(scale_fill=True)), ((1130, 930), dict(auto=True, stride=64)),
+                   ((250, 333), dict(scaleup=False, center=False, auto=True))]:
+        f = _frames(hw, 5)[0]
+        got = m.letterbox(torch.from_numpy(f).to(cuda_dev), (640, 640), **kw).cpu().numpy()
+        assert np.array_equal(got, ul(f, (640, 640), **kw)), (hw, kw)

@@ -85,3 +85,12 @@ def test_decoded_synthetic_head_round_trips_to_labels():
             same = gt[gt[:, 4] == float(row[5])]
             assert same.shape[0] > 0
             assert np.abs(same[:, :4] - row[:4].numpy()).max(1).min() < 3.0
+
+
+def test_ultralytics_shim_is_import_guarded():
+    """Ultralytics is not installed here: the shim must say so loudly instead of half-installing."""
+    import importlib.util
+    from manual_yolo_b200 import ultralytics_shim
+    if importlib.util.find_spec("ultralytics") is None:
+        with pytest.raises(ImportError):
+            ultralytics_shim.install()
