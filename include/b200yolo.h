@@ -9,7 +9,12 @@
  * reference-side stub.
  *
  * Conventions
- *  - every pointer is a DEVICE pointer owned by the caller (e.g. torch tensor.data_ptr());
+ *  - every pointer is a DEVICE-ACCESSIBLE pointer owned by the caller (e.g. torch tensor.data_ptr());
+ *    `frames` of the K5 entry points may also be PINNED HOST memory (cudaHostAlloc / torch
+ *    pin_memory(): same pointer on the device under unified addressing) -- the crops are then
+ *    read over PCIe without staging the frames (the `levels` of b200yolo_postprocess_small
+ *    likewise); b200yolo_stage_rows_h2d / b200yolo_copy2d_h2d are the only calls that take a host
+ *    source by contract;
  *    the library never allocates, frees or keeps caller memory, and has no mutable global state;
  *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
  *  - return 0 = OK, < 0 = argument error detected on the host before any launch,
@@ -175,6 +180,25 @@ int b200yolo_select_rois(const float* det, const int* det_count, int B, int max_
                          int* roi_det, int* roi_count, int roi_cap, void* stream);
 
 size_t b200yolo_workspace_bytes(int B, int cap);
+
+/* ---- host -> device staging of the source rows K1 references ------------------------------------
+ * The one entry point that takes a HOST pointer (pinned memory, or the copy is not asynchronous).
+ * Replaces the `.to(device)` of ultralytics/engine/predictor.py::BasePredictor.preprocess for the
+ * frames of a batch (detect.py:541 passes one host numpy frame per call).  Copies rows
+ * row0, row0 + row_step, ... (n_rows of them) of each of the B host frames (H x W x 3 uint8, row
+ * pitch / frame stride in bytes) into dev_rows (B, n_rows, W, 3).  manual_yolo_b200/geometry.py::
+ * referenced_rows() gives (row0, row_step, n_rows): when the vertical scale is an odd integer k the
+ * bilinear weights are (2048, 0) and K1 reads one row in k, so the staged image is passed to
+ * b200yolo_letterbox_* with H = new_h (vertical identity) and gives bit-identical output. */
+int b200yolo_stage_rows_h2d(const uint8_t* host_frames, int B, int H, int W, int64_t pitch,
+                            int64_t batch_stride, int row0, int row_step, int n_rows, uint8_t* dev_rows,
+                            int64_t dev_pitch, int64_t dev_batch_stride, void* stream);
+
+/* Generic strided host -> device copy (one 2-D DMA, pinned source): `height` runs of `width` bytes.
+ * Stages only the class channels of a host Detect-head tensor (one run per frame) when the DFL
+ * channels of the few survivors are read zero-copy by b200yolo_postprocess_small. */
+int b200yolo_copy2d_h2d(void* dev_dst, int64_t dpitch, const void* host_src, int64_t spitch, int64_t width,
+                        int64_t height, void* stream);
 
 #ifdef __cplusplus
 }

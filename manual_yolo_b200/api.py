@@ -35,14 +35,22 @@ def _require_cuda(t: torch.Tensor, name: str, dtype=None):
         raise ValueError(f"{name} must have dtype {dtype}, got {t.dtype}")
 
 
-def _frames_4d(frames: torch.Tensor):
-    _require_cuda(frames, "frames", torch.uint8)
+def _frames_4d(frames: torch.Tensor, allow_pinned=False):
+    """``allow_pinned``: K5 may read the frames straight from PINNED host memory (zero-copy over PCIe:
+    under unified addressing the device uses the same pointer); every other stage needs CUDA tensors."""
+    if allow_pinned and isinstance(frames, torch.Tensor) and not frames.is_cuda:
+        if not frames.is_pinned() or frames.dtype != torch.uint8:
+            raise ValueError("host frames must be a pinned uint8 tensor (tensor.pin_memory()); there is no CPU path")
+    else:
+        _require_cuda(frames, "frames", torch.uint8)
     squeeze = frames.dim() == 3
     if squeeze:
         frames = frames.unsqueeze(0)
     if frames.dim() != 4 or frames.shape[-1] != 3:
         raise ValueError("frames must be (H,W,3) or (B,H,W,3) uint8 BGR")
     if frames.stride(-1) != 1 or frames.stride(-2) != 3:
+        if not frames.is_cuda:
+            raise ValueError("pinned host frames must have interleaved BGR pixels (strides (.., 3, 1))")
         frames = frames.contiguous()
     return frames, squeeze
 
@@ -76,12 +84,50 @@ def letterbox(image, new_shape=(640, 640), auto=False, scale_fill=False, scaleup
     return out[0] if squeeze else out
 
 
+def stage_rows_h2d(frames_host: torch.Tensor, out: Optional[torch.Tensor] = None, new_shape=(640, 640), auto=False,
+                   scale_fill=False, scaleup=True, center=True, stride=32, device="cuda"):
+    """H2D copy of only the source rows the letterbox resize reads (``geometry.referenced_rows``): for
+    1920x1200 -> 640x400 one row in three, i.e. a third of the PCIe bytes of ``frames.to(device)``.
+    ``frames_host``: pinned (B,H,W,3) uint8.  Returns the (B,n_rows,W,3) device tensor to hand to
+    ``preprocess(..., src_hw=(H,W))``; asynchronous on the current stream."""
+    if not isinstance(frames_host, torch.Tensor) or frames_host.is_cuda or not frames_host.is_pinned():
+        raise ValueError("frames_host must be a pinned host tensor")
+    if frames_host.dtype != torch.uint8 or frames_host.dim() != 4 or frames_host.shape[-1] != 3 \
+            or not frames_host.is_contiguous():
+        raise ValueError("frames_host must be a contiguous (B,H,W,3) uint8 tensor")
+    B, H, W, _ = frames_host.shape
+    g = geometry.letterbox_geometry((H, W), new_shape, auto, scale_fill, scaleup, center, stride)
+    row0, step, n = geometry.referenced_rows(H, g["new_h"])
+    if out is None:
+        out = torch.empty((B, n, W, 3), dtype=torch.uint8, device=device)
+    elif tuple(out.shape) != (B, n, W, 3) or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous CUDA uint8 tensor of shape {(B, n, W, 3)}")
+    rc = _lib.load().b200yolo_stage_rows_h2d(_ptr(frames_host), B, H, W, frames_host.stride(1), frames_host.stride(0),
+                                             row0, step, n, _ptr(out), out.stride(1), out.stride(0), _stream())
+    _lib.check(rc, "stage_rows_h2d")
+    return out
+
+
 def preprocess(frames, new_shape=(640, 640), auto=False, scale_fill=False, scaleup=True, center=True,
-               stride=32, padding_value=114, out=None):
-    """``BasePredictor.preprocess`` drop-in, fused: uint8 BGR frames -> (B,3,H,W) fp32 RGB in [0,1]."""
+               stride=32, padding_value=114, out=None, src_hw=None):
+    """``BasePredictor.preprocess`` drop-in, fused: uint8 BGR frames -> (B,3,H,W) fp32 RGB in [0,1].
+
+    ``src_hw``: when given, ``frames`` holds only the rows ``geometry.referenced_rows(src_hw[0], new_h)``
+    names (staged by ``stage_rows_h2d``); the letterbox geometry is that of the full (H,W) source and the
+    kernel runs with a vertical scale of 1 -- bit-identical output (tests/test_gpu_letterbox.py)."""
     frames, _ = _frames_4d(frames)
     B, H, W, _ = frames.shape
-    g = geometry.letterbox_geometry((H, W), new_shape, auto, scale_fill, scaleup, center, stride)
+    if src_hw is not None:
+        if int(src_hw[1]) != W:
+            raise ValueError("staged rows must keep the source width")
+        g = geometry.letterbox_geometry(src_hw, new_shape, auto, scale_fill, scaleup, center, stride)
+        n = geometry.referenced_rows(src_hw[0], g["new_h"])[2]
+        if H != n:
+            raise ValueError(f"staged rows: expected {n} rows per frame, got {H}")
+        if n != src_hw[0] and n != g["new_h"]:
+            raise ValueError("staged rows must be the full frame or exactly new_h rows")
+    else:
+        g = geometry.letterbox_geometry((H, W), new_shape, auto, scale_fill, scaleup, center, stride)
     if out is None:
         out = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=frames.device)
     elif tuple(out.shape) != (B, 3, g["out_h"], g["out_w"]) or out.dtype != torch.float32 or not out.is_contiguous():
@@ -117,9 +163,35 @@ def _alloc_candidates(B, cap, device, out: Optional[Candidates]):
                       torch.zeros((B,), dtype=torch.int32, device=device), cap)
 
 
-def _head_levels(head, strides, in_hw, level_hw):
+def stage_head_classes_h2d(head_host: torch.Tensor, out: torch.Tensor):
+    """H2D copy of the class channels only (``head[:, 64:, :]``) of a pinned host head tensor into the
+    same-shaped device tensor ``out``: one strided DMA, (nc / (64+nc)) of the bytes.  The DFL channels of
+    ``out`` are left untouched -- pair with ``postprocess_small(head=head_host)`` (zero-copy DFL reads)."""
+    if head_host.is_cuda or not head_host.is_pinned() or head_host.dtype != torch.float32 or head_host.dim() != 3 \
+            or not head_host.is_contiguous():
+        raise ValueError("head_host must be a pinned contiguous (B,64+nc,A) float32 tensor")
+    if not out.is_cuda or out.shape != head_host.shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CUDA float32 tensor of the same shape")
+    B, no, A = head_host.shape
+    off = 4 * REG_MAX * A * 4
+    rc = _lib.load().b200yolo_copy2d_h2d(ctypes.c_void_p(out.data_ptr() + off), no * A * 4,
+                                         ctypes.c_void_p(head_host.data_ptr() + off), no * A * 4,
+                                         (no - 4 * REG_MAX) * A * 4, B, _stream())
+    _lib.check(rc, "stage_head_classes_h2d")
+    return out
+
+
+def _require_dev_accessible(t: torch.Tensor, name: str, dtype):
+    """CUDA tensor, or pinned host tensor (read zero-copy by the kernel)."""
+    if isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == dtype:
+        return
+    _require_cuda(t, name, dtype)
+
+
+def _head_levels(head, strides, in_hw, level_hw, allow_pinned=False):
     """C-ABI level descriptors for a concatenated (B,64+nc,A) head or a list of per-level tensors.
     Returns (levels, n_levels, B, nc, A, device, keepalive)."""
+    _require_cuda = _require_dev_accessible if allow_pinned else globals()["_require_cuda"]
     levels = (_lib.Level * 3)()
     if isinstance(head, (list, tuple)):
         if len(head) > 3 or len(head) != len(strides):
@@ -130,6 +202,8 @@ def _head_levels(head, strides, in_hw, level_hw):
             _require_cuda(x, "head level", torch.float32)
             if x.dim() != 4 or x.shape[0] != B or x.shape[1] != no:
                 raise ValueError("levels must be (B, 64+nc, Hi, Wi) with equal B and channels")
+            if not x.is_cuda and not x.is_contiguous():
+                raise ValueError("a pinned host head level must be contiguous")
             x = x if x.is_contiguous() else x.contiguous()
             keep.append(x)
             levels[l] = _lib.Level(x.data_ptr(), x.stride(0), x.stride(1), x.shape[2], x.shape[3], float(s))
@@ -138,6 +212,8 @@ def _head_levels(head, strides, in_hw, level_hw):
         _require_cuda(head, "head", torch.float32)
         if head.dim() != 3:
             raise ValueError("head must be (B, 64+nc, A)")
+        if not head.is_cuda and not head.is_contiguous():
+            raise ValueError("a pinned host head must be contiguous")
         head = head if head.is_contiguous() else head.contiguous()
         keep = [head]
         B, no, A = head.shape
@@ -195,7 +271,8 @@ def postprocess_small(cands: Candidates, det: "Detections", head=None, strides=(
     max_det = det.rows.shape[1]
     levels, n_levels, keep = None, 0, None
     if head is not None:
-        levels, n_levels, _, _, _, _, keep = _head_levels(head, strides, in_hw, level_hw)
+        # a pinned host head is allowed here: only the 64 DFL values of each survivor are read (zero-copy)
+        levels, n_levels, _, _, _, _, keep = _head_levels(head, strides, in_hw, level_hw, allow_pinned=True)
     rc = _lib.load().b200yolo_postprocess_small(levels, n_levels, _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count),
                                                 B, cands.cap, int(max_nms), float(iou_thres), float(max_wh),
                                                 int(bool(agnostic)), int(max_det), _ptr(scale), _ptr(det.rows),
@@ -363,7 +440,7 @@ def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=No
     large-ROI launch) for a valid crop, 0 where ``safe_crop`` would return None and -1 where the ROI is larger
     than the kernel's envelope (short side > 31 x size).
     """
-    frames, _ = _frames_4d(frames)
+    frames, _ = _frames_4d(frames, allow_pinned=True)
     _require_cuda(boxes_xyxy, "boxes_xyxy", torch.float32)
     _require_cuda(batch_idx, "batch_idx", torch.int32)
     boxes_xyxy = boxes_xyxy.contiguous()
@@ -373,9 +450,9 @@ def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=No
         raise ValueError("boxes_xyxy must be (N,4) and batch_idx (N,)")
     B, H, W, _ = frames.shape
     if out is None:
-        out = torch.empty((N, 3, size, size), dtype=torch.float32, device=frames.device)
+        out = torch.empty((N, 3, size, size), dtype=torch.float32, device=boxes_xyxy.device)
     if valid is None:
-        valid = torch.empty((N,), dtype=torch.int32, device=frames.device)
+        valid = torch.empty((N,), dtype=torch.int32, device=boxes_xyxy.device)
     rc = _lib.load().b200yolo_roi_crop_resize(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0),
                                               _ptr(boxes_xyxy), _ptr(batch_idx), _ptr(roi_count), N, int(pad),
                                               int(size), _ptr(out), _ptr(valid), _stream())
@@ -387,10 +464,10 @@ def rois_from_detections(frames, det: Detections, roi_cnt, roi_mask, nc, roi_cap
     """Pipeline form of K5: crops + resizes every detection whose class is in ``roi_mask`` straight from
     the NMS output (``roi_cnt`` = per-image counts written by ``nms_sorted``).  Returns
     (rois (roi_cap,3,size,size), roi_batch, roi_det, valid, roi_total (1,))."""
-    frames, _ = _frames_4d(frames)
+    frames, _ = _frames_4d(frames, allow_pinned=True)     # pinned host frames: crops read zero-copy over PCIe
     B, H, W, _ = frames.shape
     max_det = det.rows.shape[1]
-    dev = frames.device
+    dev = det.rows.device
     if out is None:
         out = (torch.empty((roi_cap, 3, size, size), dtype=torch.float32, device=dev),
                torch.empty((roi_cap,), dtype=torch.int32, device=dev),

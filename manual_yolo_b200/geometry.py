@@ -34,6 +34,19 @@ def letterbox_geometry(shape_hw, new_shape=(640, 640), auto=False, scale_fill=Fa
                 out_h=new_h + top + bottom, out_w=new_w + left + right, ratio=r)
 
 
+def referenced_rows(src_h, new_h):
+    """Source rows the vertical pass of ``cv2.resize(INTER_LINEAR)`` reads for src_h -> new_h, as
+    (row0, row_step, n_rows).  cv2 maps output row y to ``fy = (y + 0.5) * (src_h / new_h) - 0.5``; for an
+    odd integer scale k this is the integer ``k*y + (k-1)/2`` exactly, the fractional weight is 0 and the
+    second tap contributes nothing (coefficients 2048 / 0): one row in k is read.  Every other scale
+    reads (nearly) all rows, reported as the full range."""
+    src_h, new_h = int(src_h), int(new_h)
+    if new_h > 0 and src_h % new_h == 0 and (src_h // new_h) % 2 == 1 and src_h // new_h >= 3:
+        k = src_h // new_h
+        return (k - 1) // 2, k, new_h
+    return 0, 1, src_h
+
+
 def scale_boxes_params(img1_shape, img0_shape, ratio_pad=None):
     """``ops.scale_boxes`` gain and (pad_x, pad_y) for letterboxed shape img1 -> source shape img0."""
     if ratio_pad is None:

@@ -51,6 +51,7 @@ class Pipeline:
         g = geometry.letterbox_geometry(self.src_hw, new_shape, auto=auto, stride=max(int(s) for s in strides))
         self.geom = g
         self.in_hw = (g["out_h"], g["out_w"])
+        self.rows_plan = geometry.referenced_rows(self.src_hw[0], g["new_h"])   # (row0, step, n_rows) K1 reads
         self.level_hw = geometry.level_shapes(g["out_h"], g["out_w"], strides)
         self.A = sum(h * w for h, w in self.level_hw)
         self.cap = int(cap or self.A)
@@ -91,10 +92,28 @@ class Pipeline:
         self._hi = torch.cuda.Stream(device=self.device, priority=-1)
 
     # -- one step on device-resident inputs ------------------------------------------------------
-    def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
-        """frames: (B,H,W,3) uint8 BGR on the device; head: (B,64+nc,A) fp32 or list of level tensors."""
-        if tuple(frames.shape) != (self.B, self.src_hw[0], self.src_hw[1], 3):
-            raise ValueError(f"frames must be {(self.B, *self.src_hw, 3)}, got {tuple(frames.shape)}")
+    def __call__(self, frames: torch.Tensor, head, roi_frames: Optional[torch.Tensor] = None,
+                 dfl_head=None) -> PipelineResult:
+        """frames: (B,H,W,3) uint8 BGR on the device; head: (B,64+nc,A) fp32 or list of level tensors.
+
+        Host-fed form (``HostRunner``): ``frames`` may instead be the (B,n_rows,W,3) rows staged by
+        ``api.stage_rows_h2d`` (only what the letterbox reads); the ROI crops are then taken from
+        ``roi_frames`` -- the full frames, on the device or in PINNED host memory (zero-copy).  ``dfl_head``:
+        tensor the survivors' DFL channels are read from (default ``head``; may be the pinned host head when
+        only the class channels of ``head`` were staged)."""
+        full = (self.B, self.src_hw[0], self.src_hw[1], 3)
+        self._lb_src_hw = None
+        if tuple(frames.shape) != full:
+            if roi_frames is None or tuple(frames.shape) != (self.B, self.rows_plan[2], self.src_hw[1], 3):
+                raise ValueError(f"frames must be {full} (or the staged rows {(self.B, self.rows_plan[2], self.src_hw[1], 3)} "
+                                 f"together with roi_frames), got {tuple(frames.shape)}")
+            self._lb_src_hw = self.src_hw
+        if roi_frames is not None and tuple(roi_frames.shape) != full:
+            raise ValueError(f"roi_frames must be {full}, got {tuple(roi_frames.shape)}")
+        self._roi_frames = frames if roi_frames is None else roi_frames
+        self._dfl_head = head if dfl_head is None else dfl_head
+        if dfl_head is not None and not self.fused:
+            raise ValueError("dfl_head needs the fused sparse-regime path (cap <= 1024)")
         t = self._tick
         if self.overlap:
             main = torch.cuda.current_stream()
@@ -102,7 +121,7 @@ class Pipeline:
             self._hi.wait_stream(main)
             with torch.cuda.stream(self._side):
                 api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
-                               out=self.net_in)
+                               out=self.net_in, src_hw=self._lb_src_hw)
             with torch.cuda.stream(self._hi):
                 res = self._post_branch(frames, head, t)
             main.wait_stream(self._side)                               # join
@@ -111,7 +130,7 @@ class Pipeline:
         else:
             t("letterbox")
             api.preprocess(frames, self.new_shape, auto=self.auto, stride=max(int(s) for s in self.strides),
-                           out=self.net_in)
+                           out=self.net_in, src_hw=self._lb_src_hw)
         return self._post_branch(frames, head, t)
 
     def _post_branch(self, frames, head, t):
@@ -122,7 +141,7 @@ class Pipeline:
             api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
                                   cap=self.cap, out=self.cands, defer_boxes=True)
             t("postprocess_small")
-            det = api.postprocess_small(self.cands, self.ws.det, head, self.strides, level_hw=self.level_hw,
+            det = api.postprocess_small(self.cands, self.ws.det, self._dfl_head, self.strides, level_hw=self.level_hw,
                                         iou_thres=self.iou, agnostic=self.agnostic, max_nms=self.max_nms,
                                         max_wh=self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
                                         roi_cnt=self.roi_cnt)
@@ -137,7 +156,7 @@ class Pipeline:
                                  self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
                                  roi_cnt=self.roi_cnt)
         t("roi_crop_resize")
-        ro = api.rois_from_detections(frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
+        ro = api.rois_from_detections(self._roi_frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
         t(None)
         return PipelineResult(self.net_in, det, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
@@ -219,11 +238,12 @@ class Pipeline:
                                "raise cap (cap=None uses all anchors) or the confidence threshold")
         return mx
 
-    def make_staging(self):
+    def make_staging(self, rows_only=False, head=True):
         dev = self.device
         no = 64 + self.nc
-        return (torch.empty((self.B, self.src_hw[0], self.src_hw[1], 3), dtype=torch.uint8, device=dev),
-                torch.empty((self.B, no, self.A), dtype=torch.float32, device=dev),
+        rows = self.rows_plan[2] if rows_only else self.src_hw[0]
+        return (torch.empty((self.B, rows, self.src_hw[1], 3), dtype=torch.uint8, device=dev),
+                torch.zeros((self.B, no, self.A), dtype=torch.float32, device=dev) if head else None,
                 torch.empty((self.B, self.max_det, 6), dtype=torch.float32).pin_memory(),
                 torch.empty((self.B,), dtype=torch.int32).pin_memory(),
                 torch.empty((1,), dtype=torch.int32).pin_memory())
@@ -236,15 +256,31 @@ class Pipeline:
 
 
 class HostRunner:
-    """End-to-end driver on HOST buffers: every step copies that step's frames + head tensor from pinned
-    host memory (copy stream), runs the device path (compute stream) and reads the detections back.
-    Two staging sets let step i+1's H2D overlap step i's kernels."""
+    """End-to-end driver on HOST buffers: every step moves that step's inputs from pinned host memory (copy
+    stream), runs the device path (compute stream) and reads the detections back.  ``depth`` staging sets let
+    step i+1's H2D overlap step i's kernels.  PCIe is the bound of this path, so the bytes moved are the design:
 
-    def __init__(self, pipe: Pipeline, depth=2, head_resident=None):
+    ``stage="full"``  copies whole frames (B*H*W*3) and the whole head tensor.
+    ``stage="rows"``  copies only the source rows the letterbox reads (``geometry.referenced_rows``: a third of a
+                      1920x1200 frame) with one strided DMA, and the ROI kernel takes its crops straight from the
+                      pinned host frames (zero-copy, a few KB per ROI) -- the full-resolution frame never crosses.
+    ``dfl_zero_copy`` additionally copies only the class channels of the head; the 64 DFL values of each survivor
+                      are read zero-copy by the fused post-processing kernel (sparse regime only).
+
+    With zero-copy reads the caller must leave a submitted step's host buffers untouched until that step is done
+    (``wait(slot)`` / stream synchronisation), exactly as for the asynchronous copies."""
+
+    def __init__(self, pipe: Pipeline, depth=2, head_resident=None, stage="full", dfl_zero_copy=False):
         """``head_resident``: a device head tensor to use every step instead of copying one from the host
         (the deployment case: the Detect head is produced on the device by the backbone)."""
+        if stage not in ("full", "rows"):
+            raise ValueError("stage must be 'full' or 'rows'")
+        if dfl_zero_copy and (not pipe.fused or head_resident is not None):
+            raise ValueError("dfl_zero_copy needs the fused sparse-regime path and a host head")
         self.pipe, self.depth, self.head_resident = pipe, depth, head_resident
-        self.staging = [pipe.make_staging() for _ in range(depth)]
+        self.stage, self.dfl_zero_copy = stage, bool(dfl_zero_copy)
+        self.staging = [pipe.make_staging(rows_only=(stage == "rows"), head=head_resident is None)
+                        for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=pipe.device)
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [torch.cuda.Event() for _ in range(depth)]
@@ -254,22 +290,101 @@ class HostRunner:
         """Enqueue one step; returns the (rows, count, roi_count) pinned host tensors it will fill."""
         s = self.step % self.depth
         d_frames, d_head, h_rows, h_count, h_roi = self.staging[s]
+        p = self.pipe
         compute = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
             if self.step >= self.depth:
                 self.copy_stream.wait_event(self.free[s])
-            d_frames.copy_(frames_host, non_blocking=True)
+            if self.stage == "rows":
+                api.stage_rows_h2d(frames_host, d_frames, p.new_shape, auto=p.auto,
+                                   stride=max(int(x) for x in p.strides))
+            else:
+                d_frames.copy_(frames_host, non_blocking=True)
             if self.head_resident is None:
-                d_head.copy_(head_host, non_blocking=True)
+                if self.dfl_zero_copy:
+                    api.stage_head_classes_h2d(head_host, d_head)
+                else:
+                    d_head.copy_(head_host, non_blocking=True)
             self.ready[s].record(self.copy_stream)
         compute.wait_event(self.ready[s])
-        res = self.pipe(d_frames, d_head if self.head_resident is None else self.head_resident)
+        res = p(d_frames, d_head if self.head_resident is None else self.head_resident,
+                roi_frames=frames_host if self.stage == "rows" else None,
+                dfl_head=head_host if self.dfl_zero_copy else None)
         h_rows.copy_(res.det.rows, non_blocking=True)
         h_count.copy_(res.det.count, non_blocking=True)
         h_roi.copy_(res.roi_count, non_blocking=True)
         self.free[s].record(compute)
         self.step += 1
         return h_rows, h_count, h_roi
+
+    def wait(self, slot=None):
+        """Block until the step last submitted into ``slot`` (default: the most recent) has finished."""
+        s = (self.step - 1) % self.depth if slot is None else slot
+        self.free[s].synchronize()
+
+    def h2d_bytes_per_step(self):
+        """Bytes moved by the H2D DMAs of a step (zero-copy reads are extra: see ``zero_copy_bytes``)."""
+        p = self.pipe
+        rows = p.rows_plan[2] if self.stage == "rows" else p.src_hw[0]
+        n = p.B * rows * p.src_hw[1] * 3
+        if self.head_resident is None:
+            n += p.B * ((p.nc if self.dfl_zero_copy else 64 + p.nc)) * p.A * 4
+        return n
+
+    def zero_copy_bytes(self, det_rows, det_count):
+        """Bytes the kernels of one step pull from pinned host memory given that step's results: the crop
+        rectangles of the ROI detections (``stage='rows'``) + 256 B per detection candidate is NOT known here, so
+        the DFL part is reported by the caller from the candidate counts."""
+        if self.stage != "rows":
+            return 0
+        p, H, W = self.pipe, self.pipe.src_hw[0], self.pipe.src_hw[1]
+        total = 0
+        rows, counts = det_rows.tolist(), det_count.tolist()
+        for b, n in enumerate(counts):
+            for i in range(n):
+                x1, y1, x2, y2, _, c = rows[b][i]
+                if int(c) in p.roi_classes:
+                    cx1, cy1 = max(0, min(W - 1, int(x1 - p.pad))), max(0, min(H - 1, int(y1 - p.pad)))
+                    cx2, cy2 = max(0, min(W, int(x2 + p.pad))), max(0, min(H, int(y2 + p.pad)))
+                    total += max(0, cx2 - cx1) * max(0, cy2 - cy1) * 3
+        return total
+
+
+class BatchStream:
+    """``depth`` batches in flight on one GPU.  Slot s owns a ``Pipeline`` (its own output buffers), a stream and
+    one captured CUDA graph; ``submit()`` replays the next slot's graph on that slot's stream, so the
+    latency-bound tail of batch i (NMS, ROI crops) runs underneath the bandwidth-bound head of batch i+1
+    (letterbox, class filter) instead of leaving the SMs idle.  The reference processes one frame at a time
+    (``detect.py:530-600``); a production stream of frames has no such dependency between batches."""
+
+    def __init__(self, pipes: Sequence[Pipeline]):
+        self.pipes = list(pipes)
+        self.depth = len(self.pipes)
+        dev = self.pipes[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.pipes]
+        self.step = 0
+
+    def capture(self, inputs):
+        """``inputs``: one (frames, head) pair of static device tensors per slot (may be the same pair)."""
+        if len(inputs) != self.depth:
+            raise ValueError("one (frames, head) pair per slot")
+        for p, (f, h) in zip(self.pipes, inputs):
+            p.capture(f, h)
+
+    def submit(self) -> PipelineResult:
+        s = self.step % self.depth
+        st = self.streams[s]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            res = self.pipes[s].replay()
+        self.step += 1
+        return res
+
+    def join(self):
+        """Make the current stream wait for every slot."""
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            cur.wait_stream(st)
 
 
 def detections_to_records(det_rows, det_count, names=None, frame_offset=0):

@@ -154,3 +154,75 @@ def test_fused_postprocess_equals_general_kernels(cuda_dev):
     pipe(synth.synth_frames(3, 600, 960, seed=1).to(cuda_dev), head.to(cuda_dev))
     with pytest.raises(RuntimeError):
         pipe.check_overflow()
+
+
+def test_host_runner_stage_modes_identical(cuda_dev):
+    """HostRunner: 'full' staging, referenced-rows staging + zero-copy ROI crops, and class-channels-only head
+    staging + zero-copy DFL reads must give the oracle's results and bit-identical outputs to one another."""
+    B, nc, src_hw = 3, 64, (1200, 1920)                    # 1200 -> 400 rows: odd scale 3, one row in three staged
+    conf, iou = 0.25, 0.45
+    frames = synth.synth_frames(B, *src_hw, seed=31)
+    pipe = m.Pipeline(B, src_hw, nc, imgsz=640, conf=conf, iou=iou, device=cuda_dev, cap=1024)
+    assert pipe.rows_plan == (1, 3, 400)
+    head, _ = synth.synth_head_from_labels(B, nc, in_hw=pipe.in_hw, src_hw=src_hw, seed=31, conf_thres=conf)
+    ref = _oracle_chain(frames.numpy(), head, pipe, conf, iou)
+    fh, hh = frames.pin_memory(), head.pin_memory()
+    outs = []
+    for kw in (dict(stage="full"), dict(stage="rows"), dict(stage="rows", dfl_zero_copy=True)):
+        runner = m.HostRunner(pipe, depth=2, **kw)
+        for _ in range(3):                                   # exercises both staging slots and the free/ready events
+            rows, count, nroi = runner.submit(fh, hh)
+        runner.wait()
+        torch.cuda.synchronize()
+        res = m.PipelineResult(pipe.net_in, pipe.ws.det, pipe.cands.count, *pipe.roi_out)
+        _assert_matches(res, ref, B)
+        outs.append((rows.clone(), count.clone(), int(nroi), pipe.net_in.clone(), pipe.roi_out[0].clone()))
+        assert runner.h2d_bytes_per_step() > 0
+    full = B * 1200 * 1920 * 3 + B * 128 * 8400 * 4
+    assert m.HostRunner(pipe, stage="rows").h2d_bytes_per_step() == B * 400 * 1920 * 3 + B * 128 * 8400 * 4 < full
+    for o in outs[1:]:
+        assert torch.equal(o[1], outs[0][1]) and o[2] == outs[0][2]
+        for b in range(B):
+            assert torch.equal(o[0][b, :int(o[1][b])], outs[0][0][b, :int(o[1][b])])
+        assert torch.equal(o[3], outs[0][3]) and torch.equal(o[4][:o[2]], outs[0][4][:o[2]])
+    # a scale that is not an odd integer stages the whole frame (plan = identity) and still works
+    pipe2 = m.Pipeline(2, (900, 1600), nc, imgsz=640, conf=conf, iou=iou, device=cuda_dev, cap=1024)
+    assert pipe2.rows_plan == (0, 1, 900)
+    f2 = synth.synth_frames(2, 900, 1600, seed=32)
+    h2, _ = synth.synth_head_from_labels(2, nc, in_hw=pipe2.in_hw, src_hw=(900, 1600), seed=32, conf_thres=conf)
+    r2 = m.HostRunner(pipe2, stage="rows")
+    r2.submit(f2.pin_memory(), h2.pin_memory())
+    torch.cuda.synchronize()
+    _assert_matches(m.PipelineResult(pipe2.net_in, pipe2.ws.det, pipe2.cands.count, *pipe2.roi_out),
+                    _oracle_chain(f2.numpy(), h2, pipe2, conf, iou), 2)
+    # unpinned host memory is refused (no silent synchronous copy, no CPU path)
+    with pytest.raises(ValueError):
+        m.stage_rows_h2d(frames)
+    with pytest.raises(ValueError):
+        m.rois_from_detections(frames, pipe.ws.det, pipe.roi_cnt, pipe.roi_mask, nc, pipe.roi_cap)
+
+
+def test_batch_stream_two_in_flight(cuda_dev):
+    """BatchStream: two batches in flight on their own streams/graphs give the same results as one Pipeline."""
+    B, nc, src_hw = 2, 64, (600, 960)
+    data = []
+    for seed in (41, 42):
+        f = synth.synth_frames(B, *src_hw, seed=seed)
+        pipe0 = m.Pipeline(B, src_hw, nc, imgsz=320, conf=0.25, iou=0.7, device=cuda_dev, cap=1024)
+        h, _ = synth.synth_head_from_labels(B, nc, in_hw=pipe0.in_hw, src_hw=src_hw, seed=seed)
+        data.append((f, h, _oracle_chain(f.numpy(), h, pipe0, 0.25, 0.7)))
+    pipes = [m.Pipeline(B, src_hw, nc, imgsz=320, conf=0.25, iou=0.7, device=cuda_dev, cap=1024, overlap=True)
+             for _ in range(2)]
+    bs = m.BatchStream(pipes)
+    static = [(torch.zeros_like(f, device=cuda_dev), torch.zeros_like(h, device=cuda_dev)) for f, h, _ in data]
+    bs.capture(static)
+    for (df, dh), (f, h, _) in zip(static, data):
+        df.copy_(f); dh.copy_(h)
+    for p in pipes:
+        p.net_in.zero_()
+    torch.cuda.synchronize()
+    results = [bs.submit() for _ in range(6)]               # slots alternate: 0,1,0,1,...
+    bs.join()
+    torch.cuda.synchronize()
+    for s in range(2):
+        _assert_matches(results[4 + s], data[s][2], B)

@@ -94,3 +94,29 @@ def test_ultralytics_shim_is_import_guarded():
     if importlib.util.find_spec("ultralytics") is None:
         with pytest.raises(ImportError):
             ultralytics_shim.install()
+
+
+def test_referenced_rows_against_cv2():
+    """geometry.referenced_rows: for odd integer vertical scales cv2.resize(INTER_LINEAR) must depend on the
+    named rows only (poisoning every other row leaves the output unchanged), and the staged image with a
+    vertical scale of 1 must give the same bytes.  Other scales report the full range."""
+    import cv2
+    import numpy as np
+    from manual_yolo_b200 import geometry
+    rng = np.random.default_rng(3)
+    for (H, W), (nh, nw) in [((1200, 1920), (400, 640)), ((300, 480), (100, 160)), ((500, 800), (100, 160))]:
+        row0, step, n = geometry.referenced_rows(H, nh)
+        k = H // nh
+        assert (row0, step, n) == ((k - 1) // 2, k, nh)
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        poisoned = img.copy()
+        keep = np.zeros(H, bool)
+        keep[row0::step] = True
+        poisoned[~keep] = rng.integers(0, 256, ((~keep).sum(), W, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(poisoned, (nw, nh), interpolation=cv2.INTER_LINEAR), ref)
+        staged = np.ascontiguousarray(img[row0::step][:n])
+        assert staged.shape[0] == nh
+        assert np.array_equal(cv2.resize(staged, (nw, nh), interpolation=cv2.INTER_LINEAR), ref)
+    for H, nh in [(900, 360), (1200, 600), (543, 903), (640, 640), (1130, 640)]:     # 2.5, even, up-scale, identity
+        assert geometry.referenced_rows(H, nh) == (0, 1, H)
