@@ -163,10 +163,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_extra.json"))
     ap.add_argument("--b3", type=int, default=256)
+    ap.add_argument("--only", default="", help="comma list of: calibration,config3,config4,config1,cpu (default: all)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
-    res = {"calibration": calibration(dev), "config3_nms_heavy": config3(dev, B=args.b3),
-           "config4_roi_4096": config4(dev), "config1_single_frame": config1(dev), "cpu_oracle_threads": cpu_threads(dev)}
+    parts = {"calibration": ("calibration", lambda: calibration(dev)),
+             "config3": ("config3_nms_heavy", lambda: config3(dev, B=args.b3)),
+             "config4": ("config4_roi_4096", lambda: config4(dev)),
+             "config1": ("config1_single_frame", lambda: config1(dev)),
+             "cpu": ("cpu_oracle_threads", lambda: cpu_threads(dev))}
+    only = [x for x in args.only.split(",") if x] or list(parts)
+    res = {parts[k][0]: parts[k][1]() for k in only}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     print(json.dumps(res))

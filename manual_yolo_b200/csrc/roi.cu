@@ -35,6 +35,7 @@ constexpr int kStageBytes = 48 * 1024;  // staged crop rows (a 115x105 rank crop
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for output index `o` (triangle filter):
 // returns xmin, writes `cnt` fixed-point weights.
+template <int MAXT>
 __device__ int pil_axis(int o, int in_size, int out_size, int* coef, int cstride, int& cnt_out) {
   const double scale = __ddiv_rn((double)in_size, (double)out_size);
   const double fscale = scale < 1.0 ? 1.0 : scale;
@@ -46,7 +47,7 @@ __device__ int pil_axis(int o, int in_size, int out_size, int* coef, int cstride
   int xmax = __double2int_rz(__dadd_rn(__dadd_rn(center, support), 0.5));
   if (xmax > in_size) xmax = in_size;
   xmax -= xmin;
-  if (xmax > kMaxTaps) xmax = kMaxTaps;  // unreachable inside the supported envelope
+  if (xmax > MAXT) xmax = MAXT;  // unreachable inside the supported envelope
   double ww = 0.0;
   for (int x = 0; x < xmax; ++x) {
     double v = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
@@ -127,23 +128,17 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
     if (tid == 0 && part == 0) *valid_out = unsupported ? -1 : 0;
     return;
   }
-  if (nparts == 1 && (int64_t)cw * ch > kBigArea) {
-    // large ROI (far beyond a rank card): deferred to roi_big_kernel, which splits it over kBigParts CTAs so
-    // that one outlier cannot stall the batch; marked valid = 2 ("valid, produced by the large-ROI launch")
-    if (tid == 0) *valid_out = 2;
-    return;
-  }
   const int left = half_round_even(new_w - kS), top = half_round_even(new_h - kS);
 
   // ---- coefficient tables: threads 0..63 horizontal (own column), 64.. vertical (this CTA's rows only) ----
   if (tid < kS) {
     int cnt;
-    const int xm = pil_axis(left + tid, cw, new_w, &sm.xkT[0][tid], kS, cnt);
+    const int xm = pil_axis<kMaxTaps>(left + tid, cw, new_w, &sm.xkT[0][tid], kS, cnt);
     sm.xb[tid][0] = xm; sm.xb[tid][1] = cnt;
   } else if (tid < kS + (y_end - y_begin)) {
     const int yy = y_begin + (tid - kS);
     int cnt;
-    const int ymin = pil_axis(top + yy, ch, new_h, sm.yk[yy], 1, cnt);
+    const int ymin = pil_axis<kMaxTaps>(top + yy, ch, new_h, sm.yk[yy], 1, cnt);
     sm.yb[yy][0] = ymin; sm.yb[yy][1] = cnt;
   }
   __syncthreads();
@@ -244,90 +239,329 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
   if (tid == 0 && part == 0 && nparts == 1) *valid_out = 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast path (first launch): every ROI with <= kFTaps taps per axis (scale <= 3, i.e. short side <= 192) and
+// <= 198 referenced source columns -- every rank card and everything near it.  One CTA of 192 threads per ROI
+// and ~36 KB of shared memory, so 6 CTAs (36 warps) are resident per SM.  There is no CTA-wide staging phase:
+// each warp streams its own source rows through a private ring of 2-3 row buffers filled by 16-byte cp.async
+// (LDGSTS: no registers; rows r+6, r+12 in flight while row r is resampled), so the only CTA barriers are
+// tables -> horizontal pass -> vertical pass.  Crops taller than the uint8 strip are produced in vertical
+// tiles of output rows.  ROIs outside the envelope are marked valid = 2 and produced by roi_big_kernel (the
+// general body above, split over kBigParts CTAs).
+constexpr int kFT = 192;          // threads: 6 warps
+constexpr int kFWarps = kFT / 32;
+constexpr int kFTaps = 8;         // taps per axis (ksize = 2*ceil(scale)+1 <= 7 for scale <= 3)
+constexpr int kFRows = 116;       // uint8 strip rows: source rows one vertical tile may reference (tallest rank crop: 115)
+constexpr int kPool = 1248;       // per-warp row-buffer pool: 3 rows of <= 416 B or 2 rows of <= 624 B
+constexpr int kRingMax = 3;       // rows in flight per warp
+
+struct FastSmem {
+  int xk[kFTaps][kS];             // horizontal weights, transposed (conflict-free per warp)
+  int yk[kS][kFTaps];             // vertical weights (broadcast reads)
+  int xb[kS][2];                  // (xmin, count) per surviving output column
+  int yb[kS][2];                  // per surviving output row
+  uint8_t strip[kFRows + kFTaps][3][kS];  // horizontal-pass output (Pillow's uint8 intermediate image) + rows that
+                                          // only zero-weight taps of the unrolled vertical pass may touch
+  float lut[256];                 // v / 255 exactly as torch's fp32 division rounds it
+  __align__(16) uint8_t ring[kFWarps][kPool];
+  __align__(16) uint8_t slack[32];  // zero-weight taps of the last ring row may read (never use) up to 23 bytes past it
+  int sel[4];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(b200::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Pillow's clip8 clamps (acc >> 22) to [0,255].  For the bilinear (triangle) filter every weight is >= 0 and the
+// fixed-point weights of one output sum to at most 2^22 + taps/2, so 0 <= acc = 2^21 + sum(p_i * k_i)
+// <= 2^21 + 255 * (2^22 + 4) < 256 * 2^22: the clamp can never act and the fast path omits it (the general body
+// keeps it; both are compared bit-for-bit against PIL in tests/test_gpu_roi.py).
+__device__ __forceinline__ int shr22(int acc) { return acc >> kPrec; }
+
+// pil_axis for the fast path: <= kFTaps weights returned in registers, zero-padded, each tap evaluated once.
+__device__ __forceinline__ int pil_axis8(int o, int in_size, int out_size, int (&k)[kFTaps], int& cnt_out) {
+  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double fscale = scale < 1.0 ? 1.0 : scale;
+  const double ss = __ddiv_rn(1.0, fscale);
+  const double center = __dmul_rn((double)o + 0.5, scale);
+  int xmin = __double2int_rz(__dadd_rn(__dsub_rn(center, fscale), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = __double2int_rz(__dadd_rn(__dadd_rn(center, fscale), 0.5));
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  if (xmax > kFTaps) xmax = kFTaps;  // unreachable inside the fast envelope (scale <= 3 -> <= 7 taps)
+  double w[kFTaps], ww = 0.0;
+#pragma unroll
+  for (int x = 0; x < kFTaps; ++x) {
+    double v = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    if (v < 0.0) v = -v;
+    w[x] = (x < xmax && v < 1.0) ? __dsub_rn(1.0, v) : 0.0;
+    if (x < xmax) ww = __dadd_rn(ww, w[x]);            // same left-to-right order as Pillow's loop
+  }
+#pragma unroll
+  for (int x = 0; x < kFTaps; ++x) {
+    k[x] = 0;
+    if (x < xmax) {
+      const double q = ww != 0.0 ? __ddiv_rn(w[x], ww) : w[x];
+      k[x] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(q, (double)(1 << kPrec))));
+    }
+  }
+  cnt_out = xmax;
+  return xmin;
+}
+
+// One source row -> 6 strip bytes per lane (columns lane and lane+32, 3 channels), T taps unrolled; taps beyond a
+// column's count have weight 0 (their bytes are whatever follows in the ring: read, never used).
+template <int T>
+__device__ __forceinline__ void hrow(const uint8_t* p, const uint8_t* q, const int (&k0)[kFTaps], const int (&k1)[kFTaps],
+                                     uint8_t* so, int lane) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int a = 1 << (kPrec - 1), b = 1 << (kPrec - 1);
+#pragma unroll
+    for (int t = 0; t < T; ++t) { a += (int)p[3 * t + c] * k0[t]; b += (int)q[3 * t + c] * k1[t]; }
+    so[c * kS + lane] = (uint8_t)shr22(a);
+    so[c * kS + lane + 32] = (uint8_t)shr22(b);
+  }
+}
+
+__device__ void roi_fast_body(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B, int H, int W,
+                              int64_t pitch, int64_t bstride, int bi, int bx1, int by1, int bx2, int by2, int pad,
+                              float* __restrict__ out, int* __restrict__ valid_out, FastSmem& sm) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // ---- safe_crop (detect.py:100-113) ----
+  const int cx1 = max(0, min(W - 1, bx1 - pad)), cx2 = max(0, min(W, bx2 + pad));
+  const int cy1 = max(0, min(H - 1, by1 - pad)), cy2 = max(0, min(H, by2 + pad));
+  const int cw = cx2 - cx1, ch = cy2 - cy1;
+  bool ok = (bi >= 0 && bi < B && cw > 0 && ch > 0), unsupported = false, defer = false;
+  int new_w = kS, new_h = kS;
+  if (ok) {
+    // torchvision Resize(int): short side -> S, long side -> int(S * long / short)
+    if (cw <= ch) new_h = __double2int_rz(__ddiv_rn((double)(kS * (int64_t)ch), (double)cw));
+    else new_w = __double2int_rz(__ddiv_rn((double)(kS * (int64_t)cw), (double)ch));
+    const double sx = (double)cw / (double)new_w, sy = (double)ch / (double)new_h;
+    const int cs = (int)ceil(fmax(fmax(sx, sy), 1.0));
+    if (2 * cs + 1 > kMaxTaps) { ok = false; unsupported = true; }     // beyond the general body's envelope too
+    else if (2 * cs + 1 > kFTaps) defer = true;                        // scale > 3: general body
+  }
+  if (!ok) {
+    for (int i = tid; i < 3 * kS * kS / 4; i += kFT) reinterpret_cast<float4*>(out)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) *valid_out = unsupported ? -1 : 0;
+    return;
+  }
+  if (defer) { if (tid == 0) *valid_out = 2; return; }
+  const int left = half_round_even(new_w - kS), top = half_round_even(new_h - kS);
+
+  // ---- coefficient tables: threads 0..63 horizontal (own column), 64..127 vertical (own row); 128.. the LUT ----
+  if (tid < kS) {
+    int cnt, k[kFTaps];
+    const int xm = pil_axis8(left + tid, cw, new_w, k, cnt);
+#pragma unroll
+    for (int t = 0; t < kFTaps; ++t) sm.xk[t][tid] = k[t];
+    sm.xb[tid][0] = xm; sm.xb[tid][1] = cnt;
+  } else if (tid < 2 * kS) {
+    const int yy = tid - kS;
+    int cnt, k[kFTaps];
+    const int ymin = pil_axis8(top + yy, ch, new_h, k, cnt);
+    *reinterpret_cast<int4*>(&sm.yk[yy][0]) = make_int4(k[0], k[1], k[2], k[3]);
+    *reinterpret_cast<int4*>(&sm.yk[yy][4]) = make_int4(k[4], k[5], k[6], k[7]);
+    sm.yb[yy][0] = ymin; sm.yb[yy][1] = cnt;
+  } else {
+    for (int v = tid - 2 * kS; v < 256; v += kFT - 2 * kS) sm.lut[v] = b200::u8_div255(v);
+  }
+  __syncthreads();
+  const int x_lo = sm.xb[0][0], span = (sm.xb[kS - 1][0] + sm.xb[kS - 1][1] - x_lo) * 3;   // bounds are monotone
+  const int row_stride = (15 + span + 15) & ~15;            // worst 16-byte phase + referenced bytes, in chunks
+  const int nslots = min(kRingMax, kPool / row_stride);
+  if (nslots < 2) {                                         // uniform: row wider than the fast envelope
+    if (tid == 0) *valid_out = 2;
+    return;
+  }
+  // per-thread horizontal set-up: lane owns output columns lane and lane+32 of every row its warp resamples
+  const int xo0 = (sm.xb[lane][0] - x_lo) * 3, xo1 = (sm.xb[lane + 32][0] - x_lo) * 3;
+  const int c0 = sm.xb[lane][1], c1 = sm.xb[lane + 32][1];
+  const int cmax = __reduce_max_sync(0xffffffffu, max(c0, c1));   // warp-uniform tap class: 3, 4, 6 or 8 unrolled taps
+  const int ycmax = __reduce_max_sync(0xffffffffu, max(sm.yb[lane][1], sm.yb[lane + 32][1]));
+  int k0[kFTaps], k1[kFTaps];
+#pragma unroll
+  for (int t = 0; t < kFTaps; ++t) { k0[t] = sm.xk[t][lane]; k1[t] = sm.xk[t][lane + 32]; }   // zero beyond the count
+  uint8_t* myring = &sm.ring[wid][0];
+  const int vq = tid % 48, vph = tid / 48;                  // vertical pass: (channel, column quad), 4 row phases
+  const int vc = vq >> 4, vx = (vq & 15) * 4;
+  float* orow = out + (2 - vc) * kS * kS + vx;
+
+  int t0 = 0;
+  while (t0 < kS) {
+    // ---- vertical tile [t0, t1): the source rows [rmin, rmin + rows) it references fit the strip ----
+    const int rmin = sm.yb[t0][0];
+    int t1 = kS;
+    if (sm.yb[kS - 1][0] + sm.yb[kS - 1][1] - rmin > kFRows) {          // tall crop (not a rank card): several tiles
+      t1 = t0 + 1;
+      while (t1 < kS && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kFRows) ++t1;
+    }
+    const int rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
+    // ---- horizontal pass: warp w owns source rows w, w+6, .. of the tile ----
+    {
+      const uint8_t* row0 = frames + (int64_t)bi * bstride + (int64_t)(cy1 + rmin) * pitch + (int64_t)(cx1 + x_lo) * 3;
+      // every 16-byte chunk of every row of the tile inside the caller's buffer?  (false only for crops touching
+      // the first/last bytes of the allocation: those rows take the guarded path)
+      const bool inside = (row0 - 15 >= frames) && (row0 + (int64_t)(rows - 1) * pitch + span + 31 <= buf_hi);
+      const int64_t step = (int64_t)kFWarps * pitch;
+      const uint8_t* gi = row0 + (int64_t)wid * pitch;      // next row to issue
+      int ji = wid;
+      auto issue = [&](int slot) {
+        if (ji < rows) {
+          const int ph = (int)(reinterpret_cast<uintptr_t>(gi) & 15);
+          const int nchunk = (ph + span + 15) >> 4;         // <= row_stride / 16 <= 39
+          const uint8_t* a = gi - ph + lane * 16;
+          uint8_t* d = myring + slot * row_stride + lane * 16;
+          if (inside) {
+            if (lane < nchunk) cp_async16(d, a);
+            if (lane + 32 < nchunk) cp_async16(d + 512, a + 512);
+          } else {
+            for (int ck = lane; ck < nchunk; ck += 32, a += 512, d += 512) {
+              uint32_t* dw = reinterpret_cast<uint32_t*>(d);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dw[q] = load_word_guarded(a + 4 * q, frames, buf_hi);
+            }
+          }
+        }
+        cp_async_commit();
+        gi += step; ji += kFWarps;
+      };
+      for (int r = 0; r < nslots; ++r) issue(r);
+      int slot = 0;
+      const uint8_t* g = row0 + (int64_t)wid * pitch;       // row being resampled
+      uint8_t* so = &sm.strip[wid][0][0];
+      for (int j = wid; j < rows; j += kFWarps, g += step, so += kFWarps * 3 * kS) {
+        if (nslots == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+        __syncwarp();
+        const uint8_t* rb = myring + slot * row_stride + (int)(reinterpret_cast<uintptr_t>(g) & 15);
+        if (cmax <= 3) hrow<3>(rb + xo0, rb + xo1, k0, k1, so, lane);
+        else if (cmax <= 4) hrow<4>(rb + xo0, rb + xo1, k0, k1, so, lane);
+        else if (cmax <= 6) hrow<6>(rb + xo0, rb + xo1, k0, k1, so, lane);
+        else hrow<8>(rb + xo0, rb + xo1, k0, k1, so, lane);
+        __syncwarp();                                      // every lane is done with this slot before it is refilled
+        issue(slot);
+        slot = slot + 1 == nslots ? 0 : slot + 1;
+      }
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    // ---- vertical pass + BGR->RGB + /255: one 32-bit LDS feeds 4 accumulators per tap, one 128-bit store
+    //      per 4 outputs; taps unrolled to the crop's tap class (weights beyond a row's count are 0 and the
+    //      strip has slack rows, so the extra taps read but never contribute) ----
+    for (int yy = t0 + vph; yy < t1; yy += kFT / 48) {
+      const int ymin = sm.yb[yy][0] - rmin;
+      int a0 = 1 << (kPrec - 1), a1 = a0, a2 = a0, a3 = a0;
+      const uint8_t* sp = &sm.strip[ymin][vc][vx];
+      auto tap = [&](const uint8_t* s1, int kv) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(s1);
+        a0 += (int)(w & 0xff) * kv;
+        a1 += (int)((w >> 8) & 0xff) * kv;
+        a2 += (int)((w >> 16) & 0xff) * kv;
+        a3 += (int)(w >> 24) * kv;
+      };
+      const int4 ka = *reinterpret_cast<const int4*>(&sm.yk[yy][0]);
+      tap(sp, ka.x); tap(sp + 3 * kS, ka.y); tap(sp + 2 * 3 * kS, ka.z);
+      if (ycmax > 3) {
+        tap(sp + 3 * 3 * kS, ka.w);
+        if (ycmax > 4) {
+          const int4 kb = *reinterpret_cast<const int4*>(&sm.yk[yy][4]);
+          tap(sp + 4 * 3 * kS, kb.x); tap(sp + 5 * 3 * kS, kb.y); tap(sp + 6 * 3 * kS, kb.z); tap(sp + 7 * 3 * kS, kb.w);
+        }
+      }
+      b200::stg_stream_f4(orow + yy * kS, make_float4(sm.lut[shr22(a0)], sm.lut[shr22(a1)], sm.lut[shr22(a2)], sm.lut[shr22(a3)]));
+    }
+    if (t1 < kS) __syncthreads();                          // the strip is rewritten by the next tile
+    t0 = t1;
+  }
+  if (tid == 0) *valid_out = 1;
+}
+
 // ROI list form: boxes (N,4) float + batch_idx (N).
-__global__ void __launch_bounds__(kThreads, 2) roi_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B,
-                                                          int H, int W, int64_t pitch, int64_t bstride,
-                                                       const float* __restrict__ boxes,
-                                                       const int* __restrict__ batch_idx,
-                                                       const int* __restrict__ roi_count, int pad,
-                                                       float* __restrict__ dst, int* __restrict__ valid) {
+__global__ void __launch_bounds__(kFT, 6) roi_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B,
+                                                     int H, int W, int64_t pitch, int64_t bstride,
+                                                     const float* __restrict__ boxes, const int* __restrict__ batch_idx,
+                                                     const int* __restrict__ roi_count, int pad,
+                                                     float* __restrict__ dst, int* __restrict__ valid) {
   extern __shared__ __align__(16) uint8_t roi_smem[];
-  RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(roi_smem);
   const int r = blockIdx.x;
   if (roi_count != nullptr && r >= *roi_count) return;
   // int() truncation of the float box (detect.py:581)
-  roi_body(frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(boxes[r * 4 + 0]),
-           __float2int_rz(boxes[r * 4 + 1]), __float2int_rz(boxes[r * 4 + 2]), __float2int_rz(boxes[r * 4 + 3]), pad,
-           dst + (int64_t)r * 3 * kS * kS, valid + r, sm, 0, 1);
+  const float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)r * 4);
+  roi_fast_body(frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(bx.x), __float2int_rz(bx.y),
+                __float2int_rz(bx.z), __float2int_rz(bx.w), pad, dst + (int64_t)r * 3 * kS * kS, valid + r, sm);
 }
 
 // Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
-// the allow-list, from the per-image counts the NMS kernel wrote -- no separate selection launch.
-__global__ void __launch_bounds__(kThreads, 2) roi_det_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi,
-                                                              int B, int H, int W, int64_t pitch, int64_t bstride,
-                                                           const float* __restrict__ det,
-                                                           const int* __restrict__ det_count,
-                                                           const int* __restrict__ roi_cnt, int max_det,
-                                                           const uint32_t* __restrict__ class_mask, int nc, int pad,
-                                                           float* __restrict__ dst, int* __restrict__ roi_batch,
-                                                           int* __restrict__ roi_det, int* __restrict__ valid,
-                                                           int* __restrict__ roi_total, int roi_cap) {
+// the allow-list, from the per-image counts the NMS kernel wrote -- no separate selection launch.  The search
+// is done by warp 0 alone (shuffle scans, no CTA barriers) while the other warps wait at one barrier.
+__global__ void __launch_bounds__(kFT, 6) roi_det_kernel(const uint8_t* __restrict__ frames, const uint8_t* buf_hi,
+                                                         int B, int H, int W, int64_t pitch, int64_t bstride,
+                                                         const float* __restrict__ det,
+                                                         const int* __restrict__ det_count,
+                                                         const int* __restrict__ roi_cnt, int max_det,
+                                                         const uint32_t* __restrict__ class_mask, int nc, int pad,
+                                                         float* __restrict__ dst, int* __restrict__ roi_batch,
+                                                         int* __restrict__ roi_det, int* __restrict__ valid,
+                                                         int* __restrict__ roi_total, int roi_cap) {
   extern __shared__ __align__(16) uint8_t roi_smem[];
-  RoiSmem& sm = *reinterpret_cast<RoiSmem*>(roi_smem);
-  __shared__ int wsum[kThreads / 32];
-  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // ---- (1) which image: running prefix over roi_cnt[0..B) in chunks of kThreads ----
-  if (tid == 0) { sm.sel[0] = -1; sm.sel[1] = 0; sm.sel[2] = 0; }
-  int carry = 0;
-  for (int base = 0; base < B; base += kThreads) {
-    const int b = base + tid;
-    const int v = b < B ? roi_cnt[b] : 0;
-    int inc = v;
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(roi_smem);
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  if (tid < 32) {
+    // ---- (1) which image: running prefix over roi_cnt[0..B) in chunks of 32 ----
+    int carry = 0, selb = -1, selk = 0;
+    for (int base = 0; base < B && (selb < 0 || g == 0); base += 32) {     // CTA 0 also needs the grand total
+      const int b = base + lane;
+      const int v = b < B ? roi_cnt[b] : 0;
+      int inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int excl = carry + inc - v;
+      const unsigned hit = __ballot_sync(0xffffffffu, selb < 0 && b < B && g >= excl && g < excl + v);
+      if (hit) {
+        const int src = __ffs(hit) - 1;
+        selb = base + src;
+        selk = g - __shfl_sync(0xffffffffu, excl, src);
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 31) wsum[wid] = inc;
-    __syncthreads();
-    int wbase = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) { if (w < wid) wbase += wsum[w]; tot += wsum[w]; }
-    const int excl = carry + wbase + inc - v;
-    if (b < B && g >= excl && g < excl + v) { sm.sel[0] = b; sm.sel[1] = g - excl; }
-    carry += tot;
-    __syncthreads();
+    if (g == 0 && lane == 0) *roi_total = min(carry, roi_cap);
+    // ---- (2) the selk-th allowed detection of image selb, in kept (score) order ----
+    int seli = -1;
+    if (selb >= 0) {
+      const int n = min(det_count[selb], max_det);
+      int seen = 0;
+      for (int base = 0; base < n && seli < 0; base += 32) {
+        const int i = base + lane;
+        bool w = false;
+        if (i < n) {
+          const int c = (int)det[((int64_t)selb * max_det + i) * 6 + 5];
+          w = c >= 0 && c < nc && ((class_mask[c >> 5] >> (c & 31)) & 1u);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, w);
+        const unsigned me = __ballot_sync(0xffffffffu, w && seen + __popc(bal & ((1u << lane) - 1u)) == selk);
+        if (me) seli = base + __ffs(me) - 1;
+        seen += __popc(bal);
+      }
+    }
+    if (lane == 0) { sm.sel[0] = seli >= 0 ? selb : -1; sm.sel[1] = seli; }
   }
-  if (g == 0 && tid == 0) *roi_total = min(carry, roi_cap);
   __syncthreads();
-  const int b = sm.sel[0], k = sm.sel[1];
+  const int b = sm.sel[0], i = sm.sel[1];
   if (b < 0) return;                       // g >= number of ROIs in this batch
-  // ---- (2) the k-th allowed detection of image b, in kept (score) order ----
-  const int n = min(det_count[b], max_det);
-  int seen = 0;
-  for (int base = 0; base < n; base += kThreads) {
-    const int i = base + tid;
-    bool w = false;
-    if (i < n) {
-      const int c = (int)det[((int64_t)b * max_det + i) * 6 + 5];
-      w = c >= 0 && c < nc && ((class_mask[c >> 5] >> (c & 31)) & 1u);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, w);
-    if (lane == 0) wsum[wid] = __popc(bal);
-    __syncthreads();
-    int wbase = 0, tot = 0;
-#pragma unroll
-    for (int ww = 0; ww < kThreads / 32; ++ww) { if (ww < wid) wbase += wsum[ww]; tot += wsum[ww]; }
-    if (w && seen + wbase + __popc(bal & ((1u << lane) - 1u)) == k) sm.sel[2] = i;
-    seen += tot;
-    __syncthreads();
-    if (seen > k) break;
-  }
-  const int i = sm.sel[2];
   const float* row = det + ((int64_t)b * max_det + i) * 6;
   if (tid == 0) { roi_batch[g] = b; roi_det[g] = i; }
-  roi_body(frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
-           __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm, 0, 1);
+  roi_fast_body(frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
+                __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm);
 }
 
 // Second launch of K5: the ROIs the first launch marked valid == 2 (crop area > kBigArea).  CTA (j, part)
@@ -458,6 +692,7 @@ __global__ void __launch_bounds__(1024) select_rois_kernel(const float* __restri
 }  // namespace
 
 static size_t roi_smem_bytes() { return sizeof(RoiSmem); }
+static size_t roi_fast_smem_bytes() { return sizeof(FastSmem); }
 
 extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t pitch,
                                         int64_t batch_stride, const float* boxes, const int* batch_idx,
@@ -468,12 +703,13 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
   B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
   B200_REQUIRE(size == kS, B200YOLO_ERR_UNSUPPORTED);
   if (N == 0) return B200YOLO_OK;
-  const size_t smem = roi_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, B200YOLO_ERR_ALIGN);
+  const size_t smem = roi_smem_bytes(), fsmem = roi_fast_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
   if (e != cudaSuccess) return (int)e;
   const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
-  roi_kernel<<<N, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
-                                                           batch_idx, roi_count, pad, dst, valid);
+  roi_kernel<<<N, kFT, fsmem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
+                                                      batch_idx, roi_count, pad, dst, valid);
   e = cudaFuncSetAttribute(roi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   roi_big_kernel<<<dim3(kBigCtas, kBigParts), kThreads, smem, (cudaStream_t)stream>>>(
@@ -491,11 +727,11 @@ extern "C" int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H,
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && max_det > 0 && nc > 0 && roi_cap > 0 && pad >= 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || batch_stride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
   B200_REQUIRE(size == kS, B200YOLO_ERR_UNSUPPORTED);
-  const size_t smem = roi_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(roi_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = roi_smem_bytes(), fsmem = roi_fast_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(roi_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
   if (e != cudaSuccess) return (int)e;
   const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
-  roi_det_kernel<<<roi_cap, kThreads, smem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, det,
+  roi_det_kernel<<<roi_cap, kFT, fsmem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, det,
                                                                     det_count, roi_cnt, max_det, class_mask, nc, pad,
                                                                     dst, roi_batch, roi_det, valid, roi_total, roi_cap);
   e = cudaFuncSetAttribute(roi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
