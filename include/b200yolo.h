@@ -200,6 +200,16 @@ int b200yolo_stage_rows_h2d(const uint8_t* host_frames, int B, int H, int W, int
 int b200yolo_copy2d_h2d(void* dev_dst, int64_t dpitch, const void* host_src, int64_t spitch, int64_t width,
                         int64_t height, void* stream);
 
+/* ---- device self-test of the fast fp32 forms inside the DFL decode (test hook, no reference analogue) ----
+ * The decode must be bit-identical to torch's CPU softmax (Sleef expf_u10, true division).  Two of its
+ * inner forms are cheaper restatements; this entry proves them on the device:
+ *   mode 0: the exponent-add scaling of exp(d), d <= 0, against the two-step Sleef form for EVERY float in
+ *           [-80, 0] (n ignored);
+ *   mode 1: quotient-from-reciprocal (one rcp + Markstein correction) against IEEE division over n
+ *           pseudo-random (numerator, denominator) pairs of the softmax domain.
+ * *mismatches (device uint64, caller-zeroed) receives the number of disagreeing inputs: must stay 0. */
+int b200yolo_selftest_math(int mode, uint64_t n, uint64_t* mismatches, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

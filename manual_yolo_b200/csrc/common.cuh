@@ -105,6 +105,36 @@ __device__ __forceinline__ float expf_torch(float d) {
   if (d > 100.0f) u = __int_as_float(0x7f800000);
   return u;
 }
+// expf_torch for -80 <= d <= 0 (softmax arguments x - max): same bits, fewer instructions.  The polynomial
+// value u lies in [0.70, 1.42]; Sleef scales it by 2^q in two exact steps (ldexp2kf).  For d >= -80, q >= -116:
+// the result is a normal number, both products are exact, and the scaling is a single exponent add; the range
+// checks of the general form cannot fire.  NaN propagates (q = 0).  Checked against expf_torch for every float
+// in [-80, 0] by b200yolo_selftest_math (tests/test_gpu_decode.py).
+__device__ __forceinline__ float expf_torch_m80_0(float d) {
+  const int q = __float2int_rn(__fmul_rn(d, 1.442695040888963407359924681001892137426645954152985934135449406931f));
+  const float qf = (float)q;
+  float s = __fmaf_rn(qf, -0.693145751953125f, d);
+  s = __fmaf_rn(qf, -1.428606765330187045e-06f, s);
+  float u = 0.000198527617612853646278381f;
+  u = __fmaf_rn(u, s, 0.00139304355252534151077271f);
+  u = __fmaf_rn(u, s, 0.00833336077630519866943359f);
+  u = __fmaf_rn(u, s, 0.0416664853692054748535156f);
+  u = __fmaf_rn(u, s, 0.166666671633720397949219f);
+  u = __fmaf_rn(u, s, 0.5f);
+  u = __fadd_rn(1.0f, __fmaf_rn(__fmul_rn(s, s), u, s));
+  return __int_as_float(__float_as_int(u) + (q << 23));
+}
+
+// a / b correctly rounded, given r = RN(1/b) (__frcp_rn): q = RN(a*r) is within an ulp of a/b, the residual
+// e = a - q*b is exact in one fma, and RN(q + e*r) is the correctly rounded quotient (Markstein's theorem; needs
+// normal a, b, q -- the caller routes tiny numerators to __fdiv_rn).  Checked against __fdiv_rn over ~4e9 pairs of
+// the softmax domain by b200yolo_selftest_math.
+__device__ __forceinline__ float div_by_rcp(float a, float b, float r) {
+  const float q = __fmul_rn(a, r);
+  const float e = __fmaf_rn(-q, b, a);
+  return __fmaf_rn(e, r, q);
+}
+
 // torch CPU sigmoid: (1 + exp(-x)).reciprocal() with a true division
 __device__ __forceinline__ float sigmoid_torch(float x) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_torch(-x)));

@@ -338,14 +338,18 @@ __global__ void __launch_bounds__(256, 4) decode_vec_kernel(const FlatSegs S, co
 // Second half of the raw-head path: DFL decode of the compacted survivors.  Four lanes per candidate
 // (lane = box side): 16 bins each in one load round, softmax expectation exactly as torch computes it,
 // quad shuffle, then dist2bbox(xywh) * stride and xywh2xyxy in the reference's op order.
-__global__ void __launch_bounds__(256) box_decode_kernel(const Levels L, float* __restrict__ cand,
-                                                         const int* __restrict__ cand_anchor,
-                                                         const int* __restrict__ cand_count, int cap) {
-  const int b = blockIdx.y;
-  const int n = min(cand_count[b], cap);
+__global__ void __launch_bounds__(256, 6) box_decode_kernel(const Levels L, float* __restrict__ cand,
+                                                            const int* __restrict__ cand_anchor,
+                                                            const int* __restrict__ cand_count, int cap, int B,
+                                                            int per_image) {
   const int lane = threadIdx.x & 31, sd = threadIdx.x & 3;
-  // grid-stride over blocks of 64 survivors: few CTAs per image, none launched just to exit
-  for (int blk = blockIdx.x; blk * 64 < n; blk += gridDim.x) {
+  // flat grid-stride over (image, block of 64 survivors) pairs: the grid is one full wave of resident CTAs
+  // whatever B is, and work stays balanced when images hold different numbers of survivors
+  const int total = B * per_image;
+  for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    const int b = f / per_image, blk = f - b * per_image;
+    const int n = min(cand_count[b], cap);
+    if (blk * 64 >= n) continue;
     const int slot = blk * 64 + (threadIdx.x >> 2);
     const bool act = slot < n;
     const int a = act ? cand_anchor[(int64_t)b * cap + slot] : 0;
@@ -392,10 +396,11 @@ static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, cons
   decode_vec_kernel<RAW><<<grid, 256, 0, stream>>>(S, L, nc, cls0, conf, class_mask, cand, cand_anchor, cand_count, cap);
   if (RAW && !defer_boxes) {
     const int amax = cap < A ? cap : A;               // an image has at most min(cap, A) stored survivors
-    const int per_image = (amax + 63) / 64;           // blocks of 64 survivors; CTAs grid-stride over them
-    const int want = (4 * B200_NUM_SMS + B - 1) / B;  // enough CTAs to fill the GPU when every anchor survives
-    dim3 grid2((unsigned)(per_image < want ? per_image : (want < 2 ? 2 : want)), B);
-    box_decode_kernel<<<grid2, 256, 0, stream>>>(L, cand, cand_anchor, cand_count, cap);
+    const int per_image = (amax + 63) / 64;           // blocks of 64 survivors
+    const long long total = (long long)B * per_image;
+    const int wave = 6 * B200_NUM_SMS;                // resident CTAs (6 per SM at 40 registers)
+    box_decode_kernel<<<(unsigned)(total < wave ? total : wave), 256, 0, stream>>>(L, cand, cand_anchor, cand_count, cap, B,
+                                                                                 per_image);
   }
   return b200_launch_status();
 }
@@ -463,5 +468,50 @@ extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, i
   decode_filter_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(L, pred, channels, nc, conf_thres,
                                                                             class_mask, cand, cand_anchor, cand_count,
                                                                             cap, 0);
+  return b200_launch_status();
+}
+
+// ---- device self-test of the fast math used by the DFL decode ------------------------------------------
+// mode 0: expf_torch_m80_0(d) == expf_torch(d) for EVERY float d in [-80, 0] (the 0x42A00001 bit patterns of the
+//         negative floats up to 80.0f in magnitude; the kernel walks them all);
+// mode 1: div_by_rcp(a, b, rcp_rn(b)) == a / b for a = exp outputs in (1e-26, 1], b in [1, 16], n pairs from a
+//         counter-based generator.  mismatches: device int64, incremented per disagreeing input.
+namespace {
+__global__ void selftest_math_kernel(int mode, unsigned long long n, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (mode == 0) {
+      // negative floats: sign bit set, magnitude bits 0 .. 0x42A00000 (= 80.0f)
+      const unsigned int bits = 0x80000000u | (unsigned int)i;
+      const float d = __uint_as_float(bits);
+      const float a = b200::expf_torch_m80_0(d), b = b200::expf_torch(d);
+      bad += __float_as_uint(a) != __float_as_uint(b);
+    } else {
+      // splitmix64 -> two floats
+      unsigned long long z = i * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+      const float u1 = (float)(unsigned int)(z & 0xffffffu) * (1.0f / 16777216.0f);
+      const unsigned int hi = (unsigned int)(z >> 32);
+      const float bden = __uint_as_float(0x3f800000u + hi % (0x41800000u - 0x3f800000u + 1u));   // [1, 16]
+      const float a = b200::expf_torch_m80_0(-60.0f * u1);                                      // (8.7e-27, 1]
+      const float q1 = b200::div_by_rcp(a, bden, __frcp_rn(bden)), q2 = __fdiv_rn(a, bden);
+      bad += __float_as_uint(q1) != __float_as_uint(q2);
+      // also the raw mantissa sweep: a any normal float in [2^-80, 1]
+      const float a2 = __uint_as_float(0x17800000u + (unsigned int)((z >> 8) % (0x3f800000u - 0x17800000u + 1u)));
+      const float q3 = b200::div_by_rcp(a2, bden, __frcp_rn(bden)), q4 = __fdiv_rn(a2, bden);
+      bad += __float_as_uint(q3) != __float_as_uint(q4);
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int b200yolo_selftest_math(int mode, uint64_t n, uint64_t* mismatches, void* stream) {
+  B200_REQUIRE(mismatches, B200YOLO_ERR_NULL);
+  B200_REQUIRE(mode == 0 || mode == 1, B200YOLO_ERR_RANGE);
+  if (mode == 0) n = 0x42A00000ull + 1ull;
+  selftest_math_kernel<<<B200_NUM_SMS * 8, 256, 0, (cudaStream_t)stream>>>(mode, (unsigned long long)n,
+                                                                          (unsigned long long*)mismatches);
   return b200_launch_status();
 }

@@ -70,15 +70,26 @@ __device__ __forceinline__ float dfl_side(const float* __restrict__ p, long long
   float v[kReg];
 #pragma unroll
   for (int k = 0; k < kReg; ++k) v[k] = p[(long long)k * cs];
-  float mx = v[0];
+  float mx = v[0], mn = v[0];
 #pragma unroll
-  for (int k = 1; k < kReg; ++k) mx = fmaxf(mx, v[k]);
-  float sum = 0.f;
+  for (int k = 1; k < kReg; ++k) { mx = fmaxf(mx, v[k]); mn = fminf(mn, v[k]); }
+  float sum = 0.f, acc = 0.f;
+  // softmax = exp(x - max) / sum with torch's Sleef expf and a true division.  sum is in [1, 16] (the maximum
+  // contributes exactly 1).  When every logit is within 60 of the maximum (always, for a trained head) the cheap
+  // bit-identical forms apply: exponent-add scaling and 16 quotients from one correctly rounded reciprocal.
+  // Otherwise (tiny or subnormal exps; NaN/Inf logits fail the comparison) the general forms run.
+  if (__fsub_rn(mn, mx) >= -60.0f) {
 #pragma unroll
-  for (int k = 0; k < kReg; ++k) { v[k] = expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
-  float acc = 0.f;
+    for (int k = 0; k < kReg; ++k) { v[k] = expf_torch_m80_0(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
+    const float r = __frcp_rn(sum);
 #pragma unroll
-  for (int k = 0; k < kReg; ++k) acc = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), acc);
+    for (int k = 0; k < kReg; ++k) acc = __fmaf_rn((float)k, div_by_rcp(v[k], sum, r), acc);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kReg; ++k) { v[k] = expf_torch(__fsub_rn(v[k], mx)); sum = __fadd_rn(sum, v[k]); }
+#pragma unroll
+    for (int k = 0; k < kReg; ++k) acc = __fmaf_rn((float)k, __fdiv_rn(v[k], sum), acc);
+  }
   return acc;
 }
 

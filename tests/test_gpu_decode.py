@@ -139,3 +139,18 @@ def test_unaligned_shapes_take_the_scalar_kernel(cuda_dev):
     assert torch.equal(det.count, ref_count)
     for b in range(3):
         assert torch.equal(det.rows[b, :int(ref_count[b])], ref_rows[b, :int(ref_count[b])])
+
+
+def test_fast_math_forms_bit_identical(cuda_dev):
+    """The DFL decode's cheaper fp32 forms (exponent-add exp scaling, quotient from one correctly rounded
+    reciprocal) must be bit-identical to the Sleef / IEEE-division forms the oracle's torch ops use:
+    every float in [-80, 0] for exp, 2 x 2^31 pseudo-random pairs for the division."""
+    import ctypes
+    from manual_yolo_b200 import _lib
+    lib = _lib.load()
+    for mode, n in ((0, 0), (1, 1 << 31)):
+        bad = torch.zeros((1,), dtype=torch.int64, device=cuda_dev)
+        rc = lib.b200yolo_selftest_math(mode, n, ctypes.c_void_p(bad.data_ptr()),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "selftest_math")
+        assert int(bad.cpu()) == 0, (mode, int(bad.cpu()))
