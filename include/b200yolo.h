@@ -69,6 +69,16 @@ int b200yolo_letterbox_u8(const uint8_t* src, int B, int H, int W, int64_t src_p
                           int64_t src_batch_stride, uint8_t* dst, int outH, int outW, int new_w,
                           int new_h, int top, int left, int pad_value, void* stream);
 
+/* K1 in slice mode -- the front end of SAHI-style sliced prediction (sahi.predict.get_sliced_prediction as
+ * called at pipe.py:183-194: 640x640 windows, overlap ratio 0.2; window geometry = sahi.slicing.get_slice_bboxes,
+ * restated in manual_yolo_b200/geometry.py::slice_boxes).  Batch item f * n_slices + s is the slice_h x slice_w
+ * window of frame f whose top-left corner is (slice_xy[2s], slice_xy[2s+1]) (HOST int array); each item is
+ * letterboxed exactly like a frame of that size.  dst = (n_frames * n_slices, 3, outH, outW) float32. */
+int b200yolo_letterbox_slices_u8_to_f32(const uint8_t* frames, int n_frames, int frame_h, int frame_w,
+                                        int64_t pitch, int64_t frame_stride, const int* slice_xy, int n_slices,
+                                        int slice_h, int slice_w, float* dst, int outH, int outW, int new_w,
+                                        int new_h, int top, int left, int pad_value, int swap_rb, void* stream);
+
 /* ---- K2: Detect-head decode + confidence filter + compaction ---------------------------------
  * Replaces ultralytics/nn/modules/head.py::Detect._inference (DFL softmax expectation,
  * dist2bbox(xywh) * stride, class sigmoid) fused with the head of
@@ -178,6 +188,14 @@ int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H, int W, int
 int b200yolo_select_rois(const float* det, const int* det_count, int B, int max_det,
                          const uint32_t* class_mask, int nc, float* roi_boxes, int* roi_batch,
                          int* roi_det, int* roi_count, int roi_cap, void* stream);
+
+/* Merge step of sliced prediction: det (n_frames * n_slices, max_det, 6) / det_count from b200yolo_nms hold each
+ * slice's kept detections in slice pixels; per frame they are concatenated (slice-major, rank order), shifted by
+ * the slice origin (SAHI shift_amount) and written as candidates (cand (n_frames, cap, 6), cand_anchor =
+ * slice * max_det + rank, cand_count not clamped) for one more b200yolo_sort_topk + b200yolo_nms over the frame. */
+int b200yolo_gather_slice_detections(const float* det, const int* det_count, int n_frames, int n_slices,
+                                     int max_det, const int* slice_xy, float* cand, int* cand_anchor,
+                                     int* cand_count, int cap, void* stream);
 
 size_t b200yolo_workspace_bytes(int B, int cap);
 

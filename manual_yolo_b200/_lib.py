@@ -54,6 +54,11 @@ SIGNATURES = {
     "b200yolo_workspace_bytes": (c_size_t, [c_int, c_int]),
     "b200yolo_stage_rows_h2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, c_int,
                                         c_void_p, c_int64, c_int64, c_void_p]),
+    "b200yolo_letterbox_slices_u8_to_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, POINTER(c_int), c_int,
+                                                    c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                    c_int, c_int, c_void_p]),
+    "b200yolo_gather_slice_detections": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), c_void_p,
+                                                 c_void_p, c_void_p, c_int, c_void_p]),
     "b200yolo_selftest_math": (c_int, [c_int, ctypes.c_uint64, c_void_p, c_void_p]),
     "b200yolo_copy2d_h2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
 }

@@ -140,6 +140,56 @@ def preprocess(frames, new_shape=(640, 640), auto=False, scale_fill=False, scale
     return out
 
 
+def _slice_table(slices):
+    """[[x0,y0,x1,y1],...] (equal sizes) -> (ctypes int array of origins, n, slice_h, slice_w)."""
+    if not slices:
+        raise ValueError("no slices")
+    sw, sh = slices[0][2] - slices[0][0], slices[0][3] - slices[0][1]
+    if any(s[2] - s[0] != sw or s[3] - s[1] != sh for s in slices):
+        raise ValueError("slices must all have the same size (geometry.slice_boxes guarantees it)")
+    flat = (ctypes.c_int * (2 * len(slices)))(*[v for s in slices for v in (int(s[0]), int(s[1]))])
+    return flat, len(slices), sh, sw
+
+
+def preprocess_slices(frames, slices, new_shape=(640, 640), auto=False, scale_fill=False, scaleup=True, center=True,
+                      stride=32, padding_value=114, out=None):
+    """K1 in slice mode: the SAHI-style front end (``pipe.py:183-194``).  ``frames`` (F,H,W,3) uint8 BGR on the
+    device, ``slices`` from ``geometry.slice_boxes``; item ``f * n_slices + s`` of the result is slice ``s`` of
+    frame ``f`` letterboxed + normalised exactly as ``preprocess`` would treat that window as an image.
+    Returns (F * n_slices, 3, out_h, out_w) fp32; one launch for the whole batch."""
+    frames, _ = _frames_4d(frames)
+    F, H, W, _ = frames.shape
+    xy, ns, sh, sw = _slice_table(slices)
+    g = geometry.letterbox_geometry((sh, sw), new_shape, auto, scale_fill, scaleup, center, stride)
+    if out is None:
+        out = torch.empty((F * ns, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=frames.device)
+    elif tuple(out.shape) != (F * ns, 3, g["out_h"], g["out_w"]) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous (F*n_slices,3,out_h,out_w) float32 tensor")
+    rc = _lib.load().b200yolo_letterbox_slices_u8_to_f32(_ptr(frames), F, H, W, frames.stride(1), frames.stride(0), xy,
+                                                         ns, sh, sw, _ptr(out), g["out_h"], g["out_w"], g["new_w"],
+                                                         g["new_h"], g["top"], g["left"], int(padding_value), 1,
+                                                         _stream())
+    _lib.check(rc, "preprocess_slices")
+    return out
+
+
+def gather_slice_detections(det: "Detections", slices, n_frames, out: Optional["Candidates"] = None) -> "Candidates":
+    """Merge input of sliced prediction: the kept detections of each frame's slices (``det`` over F * n_slices
+    items, boxes in slice pixels), concatenated slice-major and shifted by the slice origins, as candidates
+    for one more NMS over the frame (``nms_candidates``).  ``anchor`` of a candidate = slice * max_det + rank."""
+    xy, ns, _, _ = _slice_table(slices)
+    max_det = det.rows.shape[1]
+    if det.rows.shape[0] != n_frames * ns:
+        raise ValueError("det must hold n_frames * n_slices items")
+    cap = ns * max_det
+    cands = _alloc_candidates(n_frames, cap, det.rows.device, out)
+    rc = _lib.load().b200yolo_gather_slice_detections(_ptr(det.rows), _ptr(det.count), n_frames, ns, max_det, xy,
+                                                      _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), cap,
+                                                      _stream())
+    _lib.check(rc, "gather_slice_detections")
+    return cands
+
+
 # ------------------------------------------------------------------------------------------------
 # K2
 # ------------------------------------------------------------------------------------------------

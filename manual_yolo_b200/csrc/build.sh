@@ -12,9 +12,9 @@ mkdir -p "$HERE/_obj"
 for f in decode_filter nms postprocess_small; do
   "$NVCC" $COMMON -fmad=false "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
 done
-for f in abi letterbox sort_topk roi; do
+for f in abi letterbox sort_topk roi slices; do
   "$NVCC" $COMMON "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
 done
 wait
-"$NVCC" -shared $ARCH -o "$OUT" "$HERE"/_obj/{abi,letterbox,decode_filter,sort_topk,nms,roi,postprocess_small}.o
+"$NVCC" -shared $ARCH -o "$OUT" "$HERE"/_obj/{abi,letterbox,decode_filter,sort_topk,nms,roi,postprocess_small,slices}.o
 echo "built $OUT"

@@ -19,6 +19,8 @@
 
 namespace {
 
+constexpr int kMaxSlices = 64;   // slices per frame in slice mode (a 1920x1200 frame at 640/0.2 has 12)
+
 struct LbParams {
   const uint8_t* src;
   void* dst;
@@ -28,6 +30,10 @@ struct LbParams {
   int row_bytes;      // W*3
   int row_smem;       // bytes reserved per staged row (>= row_bytes + 16, multiple of 16)
   int bulk_ok;        // rows are 16-byte aligned and row_bytes % 16 == 0
+  // slice mode (SAHI-style tiling, pipe.py:183-194): batch item b is slice b % ns of frame b / ns, a H x W window
+  // of the frame at (sx, sy); ns == 1 with a zero origin is the plain per-frame form
+  int ns;
+  int sx[kMaxSlices], sy[kMaxSlices];
 };
 
 // cv::resize table entry for one axis: source index and 11-bit weights (a0 for s, a1 for s+1).
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) off[k] = in[k] ? off[k] * 3 - blo : 0;   // byte offset inside the staged span
 
-  const uint8_t* frame = p.src + (int64_t)b * p.bstride + blo;
+  const int fi = b / p.ns, si = b - fi * p.ns;
+  const uint8_t* frame = p.src + (int64_t)fi * p.bstride + (int64_t)p.sy[si] * p.pitch + (int64_t)p.sx[si] * 3 + blo;
   auto prefetch = [&](int r, int s) {        // stage the source rows of CTA row r into ring slot s
     const RowInfo ri = rows[r];
     if (ri.b0 < 0 || nbytes <= 0) return;
@@ -283,8 +290,9 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
 template <typename OutT>
 int launch_letterbox(const uint8_t* src, int B, int H, int W, int64_t pitch, int64_t bstride, void* dst,
                      int outH, int outW, int new_w, int new_h, int top, int left, int pad_value, int swap_rb,
-                     void* stream) {
+                     void* stream, const int* slice_xy = nullptr, int n_slices = 1) {
   B200_REQUIRE(src && dst, B200YOLO_ERR_NULL);
+  B200_REQUIRE(n_slices >= 1 && n_slices <= kMaxSlices && B % n_slices == 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0 && new_w > 0 && new_h > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(top >= 0 && left >= 0 && top + new_h <= outH && left + new_w <= outW, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(pitch >= (int64_t)W * 3 && (B == 1 || bstride >= pitch * (int64_t)(H - 1) + (int64_t)W * 3), B200YOLO_ERR_SHAPE);
@@ -301,6 +309,12 @@ int launch_letterbox(const uint8_t* src, int B, int H, int W, int64_t pitch, int
   p.row_smem = ((p.row_bytes + 15) / 16) * 16 + 32;
   p.bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (pitch % 16 == 0) && (bstride % 16 == 0) &&
               (p.row_bytes % 16 == 0);
+  p.ns = n_slices;
+  for (int i = 0; i < kMaxSlices; ++i) {
+    p.sx[i] = (slice_xy && i < n_slices) ? slice_xy[2 * i] : 0;
+    p.sy[i] = (slice_xy && i < n_slices) ? slice_xy[2 * i + 1] : 0;
+    if (p.sx[i] % 16 != 0) p.bulk_ok = 0;          // sx * 3 bytes must keep the rows 16-byte aligned
+  }
   const size_t smem = (size_t)kStages * 2 * (size_t)p.row_smem;
   B200_REQUIRE(smem <= 200 * 1024, B200YOLO_ERR_UNSUPPORTED);
   auto kern = letterbox_kernel<OutT>;
@@ -324,6 +338,27 @@ extern "C" int b200yolo_letterbox_u8_to_f32(const uint8_t* src, int B, int H, in
                                             int swap_rb, void* stream) {
   return launch_letterbox<float>(src, B, H, W, src_pitch, src_batch_stride, dst, outH, outW, new_w, new_h, top,
                                  left, pad_value, swap_rb, stream);
+}
+
+extern "C" int b200yolo_letterbox_slices_u8_to_f32(const uint8_t* frames, int n_frames, int frame_h, int frame_w,
+                                                   int64_t pitch, int64_t frame_stride, const int* slice_xy,
+                                                   int n_slices, int slice_h, int slice_w, float* dst, int outH,
+                                                   int outW, int new_w, int new_h, int top, int left, int pad_value,
+                                                   int swap_rb, void* stream) {
+  B200_REQUIRE(frames && slice_xy && dst, B200YOLO_ERR_NULL);
+  B200_REQUIRE(n_frames > 0 && n_slices > 0 && slice_h > 0 && slice_w > 0 && frame_h >= slice_h && frame_w >= slice_w,
+               B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(n_slices <= kMaxSlices, B200YOLO_ERR_UNSUPPORTED);
+  B200_REQUIRE(pitch >= (int64_t)frame_w * 3 &&
+                   (n_frames == 1 || frame_stride >= pitch * (int64_t)(frame_h - 1) + (int64_t)frame_w * 3),
+               B200YOLO_ERR_SHAPE);
+  for (int i = 0; i < n_slices; ++i)
+    B200_REQUIRE(slice_xy[2 * i] >= 0 && slice_xy[2 * i + 1] >= 0 && slice_xy[2 * i] + slice_w <= frame_w &&
+                     slice_xy[2 * i + 1] + slice_h <= frame_h,
+                 B200YOLO_ERR_SHAPE);
+  // the per-item shape check of launch_letterbox (pitch vs slice width, stride vs slice rows) is implied by the above
+  return launch_letterbox<float>(frames, n_frames * n_slices, slice_h, slice_w, pitch, frame_stride, dst, outH, outW,
+                                 new_w, new_h, top, left, pad_value, swap_rb, stream, slice_xy, n_slices);
 }
 
 extern "C" int b200yolo_letterbox_u8(const uint8_t* src, int B, int H, int W, int64_t src_pitch,

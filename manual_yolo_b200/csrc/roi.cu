@@ -28,7 +28,6 @@ constexpr int kMaxTaps = 64;     // ksize = ceil(support)*2+1 <= 64  <=> scale <
 constexpr int kFastTaps = 8;     // taps kept in registers (scale <= 3.5: every rank-card crop)
 constexpr int kRowsMax = 128;    // uint8 strip rows staged per vertical tile (>= kMaxTaps)
 constexpr int kPrec = 22;        // Pillow PRECISION_BITS = 32 - 8 - 2
-constexpr int kBigArea = 160 * 160;  // crop pixels beyond which an ROI goes to the split (large-ROI) launch
 constexpr int kBigParts = 8;     // CTAs per large ROI: each produces kS/kBigParts output rows
 constexpr int kBigCtas = 32;     // large-ROI launch width (grid-strides over the deferred list)
 constexpr int kStageBytes = 48 * 1024;  // staged crop rows (a 115x105 rank crop needs ~37 KB)

@@ -47,6 +47,34 @@ def referenced_rows(src_h, new_h):
     return 0, 1, src_h
 
 
+def slice_boxes(image_h, image_w, slice_h=640, slice_w=640, overlap_h=0.2, overlap_w=0.2):
+    """Windows of SAHI-style sliced prediction as ``sahi.slicing.get_slice_bboxes`` lays them out (the reference
+    calls ``get_sliced_prediction(frame, slice_height=640, slice_width=640, overlap_*_ratio=0.2)``,
+    ``pipe.py:183-194``): row-major scan with steps of ``slice - int(overlap * slice)``; a window that would
+    cross the right/bottom edge is shifted back inside, so every window has the same size
+    ``(min(slice_h, image_h), min(slice_w, image_w))``.  Returns ``[[x_min, y_min, x_max, y_max], ...]``.
+    sahi is not installed in this container: restated from its published algorithm (parity unpinned)."""
+    image_h, image_w, slice_h, slice_w = int(image_h), int(image_w), int(slice_h), int(slice_w)
+    y_overlap, x_overlap = int(overlap_h * slice_h), int(overlap_w * slice_w)
+    if slice_h <= y_overlap or slice_w <= x_overlap:
+        raise ValueError("overlap must be smaller than the slice")
+    out = []
+    y_max = y_min = 0
+    while y_max < image_h:
+        x_min = x_max = 0
+        y_max = y_min + slice_h
+        while x_max < image_w:
+            x_max = x_min + slice_w
+            if y_max > image_h or x_max > image_w:
+                xmax, ymax = min(image_w, x_max), min(image_h, y_max)
+                out.append([max(0, xmax - slice_w), max(0, ymax - slice_h), xmax, ymax])
+            else:
+                out.append([x_min, y_min, x_max, y_max])
+            x_min = x_max - x_overlap
+        y_min = y_max - y_overlap
+    return out
+
+
 def scale_boxes_params(img1_shape, img0_shape, ratio_pad=None):
     """``ops.scale_boxes`` gain and (pad_x, pad_y) for letterboxed shape img1 -> source shape img0."""
     if ratio_pad is None:

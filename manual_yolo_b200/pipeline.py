@@ -387,6 +387,99 @@ class BatchStream:
             cur.wait_stream(st)
 
 
+class SlicedPipeline:
+    """SAHI-style sliced prediction of a batch of frames (the reference calls
+    ``get_sliced_prediction(frame, slice_height=640, slice_width=640, overlap ratio 0.2)``, ``pipe.py:183-194``):
+
+        K1 slice mode  every window of ``geometry.slice_boxes`` letterboxed + normalised -> the backbone's batch
+                       (F * n_slices items; one launch)
+        K2..K4         per slice, exactly as for a frame (boxes scaled to SLICE pixels)
+        gather         per frame: slices' detections concatenated and shifted by the slice origins
+        K3 + K4        one more class-aware NMS over the frame (threshold ``merge_iou``; SAHI default 0.5)
+        K5             ROI crops of the merged rank-class detections from the full frames
+
+    The Detect-head tensor of the slices is an input (the backbone stays torch)."""
+
+    def __init__(self, n_frames: int, frame_hw, nc: int, slice_hw=(640, 640), overlap=(0.2, 0.2), imgsz=640, conf=0.25,
+                 iou=0.7, merge_iou=0.5, max_det=300, agnostic=False, max_nms=30000, max_wh=7680,
+                 roi_classes: Sequence[int] = RANK_CLASS_IDS, rois_per_frame=8, pad=6, roi_size=64, strides=(8, 16, 32),
+                 device="cuda", cap=1024):
+        if not torch.cuda.is_available():
+            raise RuntimeError("manual_yolo_b200.SlicedPipeline needs a CUDA device (no CPU fallback)")
+        self.device = dev = torch.device(device)
+        self.F, self.frame_hw, self.nc = int(n_frames), (int(frame_hw[0]), int(frame_hw[1])), int(nc)
+        self.slices = geometry.slice_boxes(self.frame_hw[0], self.frame_hw[1], slice_hw[0], slice_hw[1], overlap[0], overlap[1])
+        self.S = len(self.slices)
+        self.slice_hw = (self.slices[0][3] - self.slices[0][1], self.slices[0][2] - self.slices[0][0])
+        self.new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        self.strides, self.conf, self.iou, self.merge_iou = tuple(strides), conf, iou, merge_iou
+        self.max_det, self.agnostic, self.max_nms, self.max_wh = max_det, agnostic, max_nms, max_wh
+        self.pad, self.roi_size, self.roi_classes = pad, roi_size, tuple(roi_classes)
+        g = geometry.letterbox_geometry(self.slice_hw, self.new_shape, stride=max(int(s) for s in strides))
+        self.in_hw = (g["out_h"], g["out_w"])
+        self.level_hw = geometry.level_shapes(g["out_h"], g["out_w"], strides)
+        self.A = sum(h * w for h, w in self.level_hw)
+        n_items = self.F * self.S
+        self.cap = int(cap or self.A)
+        self.fused = self.cap <= FUSED_CAP_MAX
+        self.net_in = torch.empty((n_items, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=dev)
+        self.cands = api.Candidates(torch.empty((n_items, self.cap, 6), dtype=torch.float32, device=dev),
+                                    torch.empty((n_items, self.cap), dtype=torch.int32, device=dev),
+                                    torch.zeros((n_items,), dtype=torch.int32, device=dev), self.cap)
+        self.ws = api.Workspace(n_items, self.cap, max_det, dev)               # per-slice sort/NMS
+        self.scale = api.scale_params_tensor(self.in_hw, [self.slice_hw] * n_items, dev)
+        mcap = self.S * max_det
+        self.mcands = api.Candidates(torch.empty((self.F, mcap, 6), dtype=torch.float32, device=dev),
+                                     torch.empty((self.F, mcap), dtype=torch.int32, device=dev),
+                                     torch.zeros((self.F,), dtype=torch.int32, device=dev), mcap)
+        self.mws = api.Workspace(self.F, mcap, max_det, dev)                   # merge sort/NMS
+        self.roi_cap = max(1, self.F * int(rois_per_frame))
+        self.roi_mask = api._class_mask(self.roi_classes, self.nc, dev)
+        self.roi_cnt = torch.zeros((self.F,), dtype=torch.int32, device=dev)
+        self.roi_out = (torch.zeros((self.roi_cap, 3, roi_size, roi_size), dtype=torch.float32, device=dev),
+                        torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
+                        torch.zeros((1,), dtype=torch.int32, device=dev))
+
+    def preprocess(self, frames: torch.Tensor) -> torch.Tensor:
+        """K1 slice mode alone: the (F*S,3,h,w) batch the backbone consumes."""
+        if tuple(frames.shape) != (self.F, self.frame_hw[0], self.frame_hw[1], 3):
+            raise ValueError(f"frames must be {(self.F, *self.frame_hw, 3)}, got {tuple(frames.shape)}")
+        return api.preprocess_slices(frames, self.slices, self.new_shape, stride=max(int(s) for s in self.strides),
+                                     out=self.net_in)
+
+    def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
+        """frames (F,H,W,3) uint8 BGR on the device; head (F*S, 64+nc, A): item f*S+s = slice s of frame f.
+        Returns the MERGED per-frame detections (frame pixels); ``det.anchor`` = slice * max_det + rank."""
+        self.preprocess(frames)
+        if self.fused:
+            api.decode_and_filter(head, self.strides, self.conf, level_hw=self.level_hw, cap=self.cap, out=self.cands,
+                                  defer_boxes=True)
+            det = api.postprocess_small(self.cands, self.ws.det, head, self.strides, level_hw=self.level_hw,
+                                        iou_thres=self.iou, agnostic=self.agnostic, max_nms=self.max_nms,
+                                        max_wh=self.max_wh, scale=self.scale)
+        else:
+            api.decode_and_filter(head, self.strides, self.conf, level_hw=self.level_hw, cap=self.cap, out=self.cands)
+            api.sort_candidates(self.cands, self.max_nms, self.ws)
+            det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
+                                 scale=self.scale)
+        self.slice_det = det
+        api.gather_slice_detections(det, self.slices, self.F, out=self.mcands)
+        api.sort_candidates(self.mcands, self.max_nms, self.mws)
+        merged = api.nms_sorted(self.mcands, self.mws, self.merge_iou, self.agnostic, self.max_det, self.max_nms,
+                                self.max_wh, roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
+        ro = api.rois_from_detections(frames, merged, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
+                                      self.roi_size, out=self.roi_out)
+        return PipelineResult(self.net_in, merged, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
+
+    def check_overflow(self):
+        mx = int(self.cands.count.max())
+        if mx > self.cap:
+            raise RuntimeError(f"candidate overflow: {mx} candidates in one slice > cap={self.cap}")
+        return mx
+
+
 def detections_to_records(det_rows, det_count, names=None, frame_offset=0):
     """Host-side gather into the reference's ``frame_data`` schema (``detect.py:590-598``), without the
     OCR/tracker fields the path does not produce: bbox ints are ``int()``-truncated as ``detect.py:581``."""

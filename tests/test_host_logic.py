@@ -120,3 +120,27 @@ def test_referenced_rows_against_cv2():
         assert np.array_equal(cv2.resize(staged, (nw, nh), interpolation=cv2.INTER_LINEAR), ref)
     for H, nh in [(900, 360), (1200, 600), (543, 903), (640, 640), (1130, 640)]:     # 2.5, even, up-scale, identity
         assert geometry.referenced_rows(H, nh) == (0, 1, H)
+
+
+def test_slice_boxes_layout():
+    """geometry.slice_boxes (SAHI get_slice_bboxes layout, pipe.py:183-194 parameters): equal-size windows inside
+    the image, full coverage, the documented counts, and agreement with the oracle's independent restatement."""
+    import numpy as np
+    from manual_yolo_b200 import geometry
+    from oracle import slicing
+    for (H, W), n in [((1200, 1920), 12), ((543, 770), 2), ((640, 640), 1), ((900, 1600), 6), ((100, 100), 1)]:
+        sl = geometry.slice_boxes(H, W, 640, 640, 0.2, 0.2)
+        assert sl == slicing.get_slice_bboxes_ref(H, W, 640, 640, 0.2, 0.2)
+        assert len(sl) == n
+        sizes = {(x1 - x0, y1 - y0) for x0, y0, x1, y1 in sl}
+        assert sizes == {(min(640, W), min(640, H))}
+        cover = np.zeros((H, W), bool)
+        for x0, y0, x1, y1 in sl:
+            assert 0 <= x0 < x1 <= W and 0 <= y0 < y1 <= H
+            cover[y0:y1, x0:x1] = True
+        assert cover.all()
+    assert geometry.slice_boxes(1200, 1920)[:3] == [[0, 0, 640, 640], [512, 0, 1152, 640], [1024, 0, 1664, 640]]
+    assert geometry.slice_boxes(1200, 1920)[-1] == [1280, 560, 1920, 1200]          # shifted back inside
+    import pytest
+    with pytest.raises(ValueError):
+        geometry.slice_boxes(100, 100, 10, 10, 1.0, 1.0)
