@@ -180,6 +180,7 @@ def run_ours(args, rank, world, local):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = multigpu.bind_to_gpu_numa_node(local) if world > 1 else None   # pinned host buffers local to the GPU
     pipe = m.Pipeline(BATCH, SRC_HW, NC, imgsz=IMGSZ, conf=CONF, iou=IOU, max_det=MAX_DET, device=dev,
                       cap=args.cap or None)
 
@@ -394,7 +395,8 @@ def run_ours(args, rank, world, local):
                                   "roofline_frames_per_s_per_gpu": peak * 1e9 / pipeline_bytes_frame,
                                   "frac": (value / world) / (peak * 1e9 / pipeline_bytes_frame)},
             "cpu_baseline": cpu, "clocks": clocks, "detections_last_step": n_det,
-            "candidates": {"cap": pipe.cap, "max_per_image": max_cand, "fused_postprocess": pipe.fused}}
+            "candidates": {"cap": pipe.cap, "max_per_image": max_cand, "fused_postprocess": pipe.fused},
+            "numa_node_rank0": numa}
     print(json.dumps(line), flush=True)
 
 

@@ -102,6 +102,27 @@ def config4(dev, N=4096, B=64):
     return r
 
 
+def config_n3(dev, F=16):
+    """SAHI-style sliced prediction of 1920x1200 frames (12 slices of 640x640 per frame)."""
+    sp = m.SlicedPipeline(F, (1200, 1920), 64, conf=0.25, iou=0.7, merge_iou=0.5, device=dev, cap=1024, rois_per_frame=64)
+    frames = synth.synth_frames(F, 1200, 1920, seed=0).to(dev)
+    base, _ = synth.synth_head_from_labels(sp.S, 64, in_hw=sp.in_hw, src_hw=sp.slice_hw, seed=0, conf_thres=0.25)
+    head = base.repeat(F, 1, 1).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    k1 = timed(lambda: sp.preprocess(frames), flush=flush)
+    out_bytes = F * sp.S * 3 * sp.in_hw[0] * sp.in_hw[1] * 4
+    in_bytes = F * sp.S * sp.slice_hw[0] * sp.slice_hw[1] * 3
+    k1.update(algorithmic_bytes=in_bytes + out_bytes, algo_GBps=(in_bytes + out_bytes) / (k1["us_median"] * 1e-6) / 1e9)
+    step = timed(lambda: sp(frames, head), flush=flush)
+    res = sp(frames, head)
+    torch.cuda.synchronize()
+    return {"frames": F, "slices_per_frame": sp.S, "letterbox_slices": k1, "sliced_step": step,
+            "frames_per_s": F / (step["us_median"] * 1e-6), "slices_per_s": F * sp.S / (step["us_median"] * 1e-6),
+            "merged_detections_per_frame": float(res.det.count.float().mean()),
+            "slice_detections_per_frame": float(sp.slice_det.count.float().sum() / F),
+            "l2": "L2 flushed between iterations; eager launches"}
+
+
 def config1(dev):
     out = {}
     frame = synth.synth_frames(1, 900, 1600, seed=0)
@@ -163,13 +184,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_extra.json"))
     ap.add_argument("--b3", type=int, default=256)
-    ap.add_argument("--only", default="", help="comma list of: calibration,config3,config4,config1,cpu (default: all)")
+    ap.add_argument("--only", default="", help="comma list of: calibration,config3,config4,config1,n3,cpu (default: all)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     parts = {"calibration": ("calibration", lambda: calibration(dev)),
              "config3": ("config3_nms_heavy", lambda: config3(dev, B=args.b3)),
              "config4": ("config4_roi_4096", lambda: config4(dev)),
              "config1": ("config1_single_frame", lambda: config1(dev)),
+             "n3": ("n3_sliced_prediction", lambda: config_n3(dev)),
              "cpu": ("cpu_oracle_threads", lambda: cpu_threads(dev))}
     only = [x for x in args.only.split(",") if x] or list(parts)
     res = {parts[k][0]: parts[k][1]() for k in only}

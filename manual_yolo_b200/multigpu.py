@@ -32,6 +32,31 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore its pinned host allocations: first touch) to the CPUs of the NUMA node the
+    GPU hangs off, so that the H2D DMA of the host-fed path never crosses the socket interconnect.  Linux sysfs
+    only; returns the node id, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(os.path.join(path, "numa_node")).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def my_frames(n_frames: int, rank: int, world: int):
     """Frame index range [lo, hi) this rank processes."""
     return geometry.shard_range(n_frames, rank, world)
