@@ -117,8 +117,12 @@ int b200yolo_filter_decoded(const float* pred, int B, int channels, int nc, int 
 /* ---- K3: per-image sort (score descending, anchor ascending on ties) + max_nms cap ----------
  * Replaces the stable descending sort inside torchvision.ops.nms and UL's `n > max_nms` cap.
  * order: (B, cap) int32, order[b][r] = slot of rank r for r < min(count, cap, max_nms).
- * workspace: b200yolo_workspace_bytes(B, cap) bytes, 16-byte aligned (used when cap exceeds the
- * shared-memory path). */
+ * workspace: b200yolo_workspace_bytes(B, cap) bytes, 16-byte aligned; pass the SAME workspace to b200yolo_nms.
+ * It starts with a header (per image: how many entries of order[] are in order, and a fallback flag).  For
+ * cap > 2048 only the best 2048 entries of an image are ordered (radix select + bitonic sort): greedy NMS stops at
+ * max_det keeps long before it needs more; if it ever does, b200yolo_nms re-sorts that image completely and
+ * re-runs it, so results are exact in every case.  workspace may be NULL for cap <= 12288: everything is then
+ * fully sorted (no header, no fallback). */
 int b200yolo_sort_topk(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap,
                        int max_nms, int* order, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -12,11 +12,15 @@
 //     division; the fp32 ovr is compared against the DOUBLE threshold; NaN (0/0) never suppresses;
 //   * kept boxes come out in score order, so stopping after max_det keeps == `i[:max_det]`.
 //
-// One CTA per image; sorted offset boxes live in shared memory.  Boxes are processed in chunks of 64
-// (sorted order): (A) the 64x64 intra-chunk IoU bitmask is built in parallel (4 pairs per thread,
-// rows merged with warp shuffles), (B) one thread resolves the chunk serially over the mask words
-// (ffs over the alive bits), (C) the chunk's kept boxes are applied to every later box in parallel.
-// Total IoU work <= kept * n instead of n^2/2.  Compiled with -fmad=false.
+// One CTA per image.  The sorted list is consumed in WINDOWS of kWindow boxes: greedy NMS in score order only
+// ever needs the prefix it takes to collect max_det keeps (a few hundred boxes even when 8400 pass the confidence
+// filter), so neither the gather of the sorted rows nor the suppression sweep touches the rest.  A window lives in
+// shared memory (21 B per box); the kept boxes of earlier windows (<= max_det, 20 B each) stay resident and a new
+// window is first tested against them.  Inside a window boxes are processed in chunks of 64 (sorted order): (A) the
+// 64x64 intra-chunk IoU bitmask is built in parallel (4 pairs per thread, rows merged with warp shuffles), (B) one
+// thread resolves the chunk serially over the mask words (ffs over the alive bits), (C) the chunk's kept boxes
+// are applied to every later box of the window in parallel.  ~30 KB of shared memory per CTA: several images per
+// SM, so a batch of 256 images is one wave.  Compiled with -fmad=false.
 
 #include "nms_common.cuh"
 
@@ -28,9 +32,7 @@ using b200::may_overlap;
 using b200::scale_clip;
 
 constexpr int kChunk = 64;
-constexpr int kSmemBoxesMax = 10240;   // (16 + 1 + 4) B per box + keep list <= 227 KB
-
-
+constexpr int kWindow = 1024;          // sorted boxes resident at a time
 
 template <int NT>
 __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
@@ -39,13 +41,15 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
                                                  int max_det, const float* __restrict__ scale,
                                                  float* __restrict__ out, int* __restrict__ out_anchor,
                                                  int* __restrict__ out_count, const uint32_t* __restrict__ roi_mask,
-                                                 int roi_nc, int* __restrict__ roi_cnt, float4* __restrict__ ws,
-                                                 int smem_boxes) {
+                                                 int roi_nc, int* __restrict__ roi_cnt, int* __restrict__ hdr, int B,
+                                                 int pass) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float4* sbox = reinterpret_cast<float4*>(smem_raw);
-  uint8_t* removed = reinterpret_cast<uint8_t*>(sbox + smem_boxes);   // [smem_boxes or n]
-  int* keep = reinterpret_cast<int*>(removed + ((smem_boxes + 15) & ~15));  // [max_det]
-  int* smeta = keep + ((max_det + 3) & ~3);                                 // [smem_boxes] class id, or -1
+  float4* box = reinterpret_cast<float4*>(smem_raw);                  // [kWindow] class-offset boxes of the window
+  float4* kbox = box + kWindow;                                       // [max_det] kept boxes (all windows)
+  int* meta = reinterpret_cast<int*>(kbox + ((max_det + 3) & ~3));    // [kWindow] class id, or -1
+  int* kmeta = meta + kWindow;                                        // [max_det]
+  int* keep = kmeta + ((max_det + 3) & ~3);                           // [max_det] sorted index of each kept box
+  uint8_t* rem = reinterpret_cast<uint8_t*>(keep + ((max_det + 3) & ~3));   // [kWindow]
   __shared__ unsigned long long mask[kChunk];
   __shared__ unsigned rem_bits[2];
   __shared__ unsigned long long kept_bits_s;
@@ -55,91 +59,100 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
   __shared__ unsigned long long always_s;      // kept boxes that must be tested against every class (meta -1)
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = min(min(min(cand_count[b], cap), max_nms), B200YOLO_MAX_SORT);
+  if (pass == 1 && !(hdr && hdr[B + b])) return;       // fallback launch: only the images flagged by pass 0
+  const int n_all = min(min(min(cand_count[b], cap), max_nms), B200YOLO_MAX_SORT);
+  // hdr[b] = how many entries of order[] the sort put in order (dense regime: the best 2048 only)
+  const int n = hdr ? min(n_all, hdr[b]) : n_all;
   const float* crow = cand + (int64_t)b * cap * 6;
   const int* orow = order + (int64_t)b * cap;
   if (n <= 0) {
     if (tid == 0) { out_count[b] = 0; if (roi_cnt) roi_cnt[b] = 0; }
     return;
   }
-  float4* box = sbox;
-  uint8_t* rem = removed;
-  int* meta = smeta;
-  const bool use_meta = n <= smem_boxes;   // oversize images (workspace path) always run the full IoU test
-  if (n > smem_boxes) {  // oversize image: boxes + flags in the workspace (L2-resident)
-    box = ws + (int64_t)b * (cap + (cap + 15) / 16);
-    rem = reinterpret_cast<uint8_t*>(box + cap);
-  }
-  for (int r = tid; r < n; r += NT) {
-    const float* row = crow + (int64_t)orow[r] * 6;
-    const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
-    box[r] = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
-    rem[r] = 0;
-    if (use_meta) meta[r] = box_meta(row, max_wh, agnostic);
-  }
   if (tid == 0) { kcount_s = 0; roi_s = 0; }
   __syncthreads();
 
-  for (int s = 0; s < n; s += kChunk) {
-    const int m = min(kChunk, n - s);
-    // ---- (A) intra-chunk mask: thread -> row i = t/16, columns j = (t%16)*4 .. +3 ----
-    for (int t = tid; t < kChunk * 16; t += NT) {
-      const int i = t >> 4, jg = t & 15;
-      unsigned nib = 0;
-      if (i < m) {
-        const float4 bi = box[s + i];
+  for (int w0 = 0; w0 < n; w0 += kWindow) {
+    const int wn = min(kWindow, n - w0);
+    const int kprev = kcount_s;               // keeps collected in earlier windows (uniform: read after a barrier)
+    // ---- load the window; test it against the kept boxes of earlier windows ----
+    for (int r = tid; r < wn; r += NT) {
+      const float* row = crow + (int64_t)orow[w0 + r] * 6;
+      const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
+      const float4 bj = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
+      const int mj = box_meta(row, max_wh, agnostic);
+      bool dead = false;
+      for (int k = 0; k < kprev && !dead; ++k) {
+        if (!may_overlap(kmeta[k], mj)) continue;
+        const float4 bi = kbox[k];
         const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+        dead = iou_suppresses(bi, ai, bj, thr);
+      }
+      box[r] = bj; meta[r] = mj; rem[r] = dead ? 1 : 0;
+    }
+    __syncthreads();
+
+    bool done = false;
+    for (int s = 0; s < wn; s += kChunk) {
+      const int m = min(kChunk, wn - s);
+      // ---- (A) intra-chunk mask: thread -> row i = t/16, columns j = (t%16)*4 .. +3 ----
+      for (int t = tid; t < kChunk * 16; t += NT) {
+        const int i = t >> 4, jg = t & 15;
+        unsigned nib = 0;
+        if (i < m) {
+          const float4 bi = box[s + i];
+          const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = jg * 4 + u;
-          if (j > i && j < m && (!use_meta || may_overlap(meta[s + i], meta[s + j])) &&
-              iou_suppresses(bi, ai, box[s + j], thr))
-            nib |= 1u << u;
+          for (int u = 0; u < 4; ++u) {
+            const int j = jg * 4 + u;
+            if (j > i && j < m && may_overlap(meta[s + i], meta[s + j]) && iou_suppresses(bi, ai, box[s + j], thr))
+              nib |= 1u << u;
+          }
         }
-      }
-      unsigned lo = jg < 8 ? nib << (jg * 4) : 0u;
-      unsigned hi = jg >= 8 ? nib << ((jg - 8) * 4) : 0u;
+        unsigned lo = jg < 8 ? nib << (jg * 4) : 0u;
+        unsigned hi = jg >= 8 ? nib << ((jg - 8) * 4) : 0u;
 #pragma unroll
-      for (int o = 1; o < 16; o <<= 1) {
-        lo |= __shfl_xor_sync(0xffffffffu, lo, o);
-        hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+        for (int o = 1; o < 16; o <<= 1) {
+          lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+          hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+        }
+        if (jg == 0) mask[i] = ((unsigned long long)hi << 32) | lo;
       }
-      if (jg == 0) mask[i] = ((unsigned long long)hi << 32) | lo;
-    }
-    if (wid < 2) {
-      const int j = wid * 32 + lane;
-      const unsigned bits = __ballot_sync(0xffffffffu, j < m && rem[s + j] != 0);
-      if (lane == 0) rem_bits[wid] = bits;
-    }
-    __syncthreads();
-    // ---- (B) serial resolve of the chunk ----
-    if (tid == 0) {
-      const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-      unsigned long long alive = valid & ~(((unsigned long long)rem_bits[1] << 32) | rem_bits[0]);
-      unsigned long long kept = 0;
-      int kc = kcount_s;
-      while (alive && kc < max_det) {
-        const int i = __ffsll((long long)alive) - 1;
-        kept |= 1ull << i;
-        keep[kc++] = s + i;
-        alive &= ~mask[i];
-        alive &= ~(1ull << i);
+      if (wid < 2) {
+        const int j = wid * 32 + lane;
+        const unsigned bits = __ballot_sync(0xffffffffu, j < m && rem[s + j] != 0);
+        if (lane == 0) rem_bits[wid] = bits;
       }
-      kept_bits_s = kept;
-      kcount_s = kc;
-    }
-    __syncthreads();
-    const int kc = kcount_s;
-    if (kc >= max_det) break;
-    // ---- (C) apply this chunk's kept boxes to all later boxes ----
-    // Class-aware shortcut (exact, see box_meta): a later box only needs the kept boxes of its own class.
-    // The chunk's kept boxes are bucketed by (class & 127) into 64-bit masks, so a thread visits 0-2
-    // kept boxes per later box instead of up to 64.
-    const unsigned long long kept = kept_bits_s;
-    if (kept) {
-      if (use_meta) {
+      __syncthreads();
+      // ---- (B) serial resolve of the chunk ----
+      if (tid == 0) {
+        const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+        unsigned long long alive = valid & ~(((unsigned long long)rem_bits[1] << 32) | rem_bits[0]);
+        unsigned long long kept = 0;
+        int kc = kcount_s;
+        while (alive && kc < max_det) {
+          const int i = __ffsll((long long)alive) - 1;
+          kept |= 1ull << i;
+          keep[kc] = w0 + s + i;
+          kbox[kc] = box[s + i];
+          kmeta[kc] = meta[s + i];
+          ++kc;
+          alive &= ~mask[i];
+          alive &= ~(1ull << i);
+        }
+        kept_bits_s = kept;
+        kcount_s = kc;
+      }
+      __syncthreads();
+      if (kcount_s >= max_det) { done = true; break; }
+      // ---- (C) apply this chunk's kept boxes to all later boxes of the window ----
+      // Class-aware shortcut (exact, see box_meta): a later box only needs the kept boxes of its own class.
+      // The chunk's kept boxes are bucketed by (class & 127) into 64-bit masks, so a thread visits 0-2
+      // kept boxes per later box instead of up to 64.
+      const unsigned long long kept = kept_bits_s;
+      if (kept && s + kChunk < wn) {
         if (tid < 128) cmask[tid] = 0ull;
-        if (tid == 128) always_s = 0ull;
+        if (tid == 128 % NT) always_s = 0ull;
         __syncthreads();
         if (tid < kChunk && ((kept >> tid) & 1ull)) {
           const int mi = meta[s + tid];
@@ -147,40 +160,44 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
           else atomicOr(&cmask[mi & 127], 1ull << tid);
         }
         __syncthreads();
-      }
-      for (int j = s + kChunk + tid; j < n; j += NT) {
-        if (rem[j]) continue;
-        const float4 bj = box[j];
-        unsigned long long kb = kept;
-        int mj = -1;
-        if (use_meta) {
-          mj = meta[j];
-          if (mj >= 0) kb = cmask[mj & 127] | always_s;
-        }
-        while (kb) {
-          const int i = __ffsll((long long)kb) - 1;
-          kb &= kb - 1;
-          if (use_meta && !may_overlap(meta[s + i], mj)) continue;   // bucket collision (class & 127)
-          const float4 bi = box[s + i];
-          const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-          if (iou_suppresses(bi, ai, bj, thr)) { rem[j] = 1; break; }
+        for (int j = s + kChunk + tid; j < wn; j += NT) {
+          if (rem[j]) continue;
+          const float4 bj = box[j];
+          const int mj = meta[j];
+          unsigned long long kb = mj >= 0 ? (cmask[mj & 127] | always_s) : kept;
+          while (kb) {
+            const int i = __ffsll((long long)kb) - 1;
+            kb &= kb - 1;
+            if (!may_overlap(meta[s + i], mj)) continue;   // bucket collision (class & 127)
+            const float4 bi = box[s + i];
+            const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+            if (iou_suppresses(bi, ai, bj, thr)) { rem[j] = 1; break; }
+          }
         }
       }
+      __syncthreads();
     }
+    if (done) break;
     __syncthreads();
   }
   __syncthreads();
-  // ---- outputs: un-offset rows in kept order ----
   const int kc = kcount_s;
-  float gain = 1.f, padx = 0.f, pady = 0.f, w0 = 0.f, h0 = 0.f;
-  if (scale) { gain = scale[b * 5 + 0]; padx = scale[b * 5 + 1]; pady = scale[b * 5 + 2]; w0 = scale[b * 5 + 3]; h0 = scale[b * 5 + 4]; }
+  if (n < n_all && kc < max_det) {
+    // the ordered prefix ran out before max_det keeps: this image needs the full sort.  Flag it; b200yolo_nms
+    // launches the fallback pair (full sort + this kernel with pass = 1) right behind this launch.
+    if (tid == 0) hdr[B + b] = 1;
+    return;
+  }
+  // ---- outputs: un-offset rows in kept order ----
+  float gain = 1.f, padx = 0.f, pady = 0.f, w0s = 0.f, h0s = 0.f;
+  if (scale) { gain = scale[b * 5 + 0]; padx = scale[b * 5 + 1]; pady = scale[b * 5 + 2]; w0s = scale[b * 5 + 3]; h0s = scale[b * 5 + 4]; }
   for (int r = tid; r < kc; r += NT) {
     const int slot = orow[keep[r]];
     const float* row = crow + (int64_t)slot * 6;
     float x1 = row[0], y1 = row[1], x2 = row[2], y2 = row[3];
     if (scale) {
-      x1 = scale_clip(x1, padx, gain, w0); y1 = scale_clip(y1, pady, gain, h0);
-      x2 = scale_clip(x2, padx, gain, w0); y2 = scale_clip(y2, pady, gain, h0);
+      x1 = scale_clip(x1, padx, gain, w0s); y1 = scale_clip(y1, pady, gain, h0s);
+      x2 = scale_clip(x2, padx, gain, w0s); y2 = scale_clip(y2, pady, gain, h0s);
     }
     float* o = out + ((int64_t)b * max_det + r) * 6;
     o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = row[4]; o[5] = row[5];
@@ -215,14 +232,12 @@ extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int
   B200_REQUIRE(cap <= B200YOLO_MAX_SORT && max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
   B200_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, B200YOLO_ERR_RANGE);
   B200_REQUIRE(roi_cnt == nullptr || (roi_class_mask != nullptr && roi_nc > 0), B200YOLO_ERR_NULL);
-  if (cap > kSmemBoxesMax) {
-    B200_REQUIRE(workspace, B200YOLO_ERR_NULL);
-    B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
-    B200_REQUIRE(workspace_bytes >= (size_t)B * ((size_t)cap + (cap + 15) / 16) * 16, B200YOLO_ERR_WORKSPACE);
-  }
-  const int smem_boxes = cap < kSmemBoxesMax ? cap : kSmemBoxesMax;
-  const size_t smem = (size_t)smem_boxes * 16 + (((size_t)smem_boxes + 15) & ~(size_t)15) +
-                      (((size_t)max_det + 3) & ~(size_t)3) * 4 + (size_t)smem_boxes * 4;
+  // workspace header (see sort_topk.cu): present iff the same workspace was given to b200yolo_sort_topk
+  const bool have_hdr = workspace != nullptr && workspace_bytes >= b200yolo_workspace_bytes(B, cap);
+  if (workspace) B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
+  int* hdr = have_hdr ? reinterpret_cast<int*>(workspace) : nullptr;
+  const size_t md4 = ((size_t)max_det + 3) & ~(size_t)3;
+  const size_t smem = (size_t)kWindow * 16 + md4 * 16 + (size_t)kWindow * 4 + md4 * 4 + md4 * 4 + (size_t)kWindow;
   cudaStream_t s = (cudaStream_t)stream;
   if (cap <= 1024) {
     constexpr int NT = 256;
@@ -232,16 +247,27 @@ extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int
       if (e != cudaSuccess) return (int)e;
     }
     kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt,
-                             (float4*)workspace, smem_boxes);
+                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, hdr, B, 0);
   } else {
-    constexpr int NT = 1024;
+    constexpr int NT = 512;
     auto kern = nms_kernel<NT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
     kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt,
-                             (float4*)workspace, smem_boxes);
+                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, hdr, B, 0);
+    if (have_hdr && cap > 2048) {
+      // dense regime: the sort ordered only the best 2048 entries per image.  Images whose NMS ran out of them
+      // (flag raised above) are re-done exactly: full sort, then NMS again -- both launches exit at once otherwise.
+      int rc = b200_launch_status();
+      if (rc != B200YOLO_OK) return rc;
+      rc = b200_sort_launch(cand, cand_anchor, cand_count, B, cap, max_nms, const_cast<int*>(order), workspace,
+                            workspace_bytes, 1, s);
+      if (rc != B200YOLO_OK) return rc;
+      kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
+                               max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, hdr, B, 1);
+    }
   }
   return b200_launch_status();
 }

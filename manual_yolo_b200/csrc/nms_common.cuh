@@ -4,6 +4,11 @@
 
 #include "common.cuh"
 
+// sort_topk.cu: pass 0 = the regular per-image sort (dense regime: only the best 2048 entries are ordered, the count
+// goes to the workspace header), pass 1 = full sort of the images whose fallback flag the NMS raised.
+int b200_sort_launch(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
+                     int* order, void* workspace, size_t workspace_bytes, int pass, cudaStream_t s);
+
 namespace b200 {
 
 // Sort key: ascending key order == score descending, anchor ascending on ties (the reference's stable

@@ -13,6 +13,12 @@
 //   n >  512 : LSD radix sort, 8-bit digits over key bits 16..63, per-warp histograms; each warp
 //              owns a contiguous key segment so the scatter is stable (match_any ranks within a
 //              32-key row); passes whose digit is uniform across the image are skipped.
+//   cap > 2048 (dense regime): sort_select_kernel -- greedy NMS consumes the sorted list from the top and stops
+//              at max_det keeps, so only the best kSelK = 2048 keys are put in order: a 6-pass MSD radix SELECT
+//              finds the kSelK-th smallest key, the keys up to it are compacted and bitonic-sorted.  The number
+//              of sorted entries goes to the workspace header; if the NMS ever runs out of them before max_det
+//              keeps, it raises a per-image flag and b200yolo_nms re-runs that image with the full sort above
+//              (exact in every case, one cheap path in the common one).
 // Latency-bound: reported in microseconds, not GB/s.
 
 #include "nms_common.cuh"
@@ -30,7 +36,7 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
                                                        const int* __restrict__ cand_anchor,
                                                        const int* __restrict__ cand_count, int cap, int max_nms,
                                                        int* __restrict__ order, uint64_t* __restrict__ ws,
-                                                       int smem_keys) {
+                                                       int smem_keys, int* __restrict__ hdr, int B, int pass) {
   constexpr int W = NT / 32;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* sA = reinterpret_cast<uint64_t*>(smem_raw);
@@ -39,9 +45,11 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
   __shared__ uint32_t warp_tot[32];
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (pass == 1 && !(hdr && hdr[B + b])) return;           // fallback launch: only the images the NMS flagged
   const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
+  const int n_out = min(max(n, 0), max_nms);
+  if (hdr && tid == 0) { hdr[b] = n_out; if (pass == 0) hdr[B + b] = 0; }   // every entry sorted; no fallback pending
   if (n <= 0) return;
-  const int n_out = min(n, max_nms);
   const float* crow = cand + (int64_t)b * cap * 6;
   const int* arow = cand_anchor + (int64_t)b * cap;
   int* orow = order + (int64_t)b * cap;
@@ -146,13 +154,151 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
   for (int r = tid; r < n_out; r += NT) orow[r] = (int)(src[r] & 0xffff);
 }
 
+// ---- dense regime: select the best kSelK keys, sort only those ----------------------------------------
+constexpr int kSelK = 2048;
+
+__device__ __forceinline__ void bitonic_sort_2048(uint64_t* s, int tid, int nt) {
+  for (int k = 2; k <= kSelK; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < kSelK / 2; t += nt) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+        const uint64_t a = s[i], c = s[l];
+        if ((a > c) == ((i & k) == 0)) { s[i] = c; s[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __restrict__ cand,
+                                                              const int* __restrict__ cand_anchor,
+                                                              const int* __restrict__ cand_count, int cap, int max_nms,
+                                                              int* __restrict__ order, uint64_t* __restrict__ ws,
+                                                              int keys_in_smem, int* __restrict__ hdr, int B) {
+  constexpr int NT = 1024;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* sB = reinterpret_cast<uint64_t*>(smem_raw);          // [kSelK] the selected keys
+  uint64_t* src = sB + kSelK;                                     // [cap] all keys (shared memory, or the workspace)
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long sel_prefix;
+  __shared__ int sel_k, cursor;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
+  const int n_out = min(max(n, 0), max_nms);
+  if (tid == 0) { hdr[b] = min(n_out, kSelK); hdr[B + b] = 0; }
+  if (n <= 0) return;
+  if (!keys_in_smem) src = ws + (int64_t)b * 2 * cap;
+  const float* crow = cand + (int64_t)b * cap * 6;
+  const int* arow = cand_anchor + (int64_t)b * cap;
+  int* orow = order + (int64_t)b * cap;
+
+  if (n <= kSelK) {
+    // everything fits the bitonic network: pad with the largest key
+    for (int i = tid; i < kSelK; i += NT) sB[i] = i < n ? make_key(crow[i * 6 + 4], arow[i], i) : ~0ull;
+    __syncthreads();
+  } else {
+    for (int i = tid; i < n; i += NT) src[i] = make_key(crow[i * 6 + 4], arow[i], i);
+    if (tid == 0) cursor = 0;
+    // MSD radix select over key bits [16, 64): prefix = top bits of the kSelK-th smallest key so far
+    unsigned long long prefix = 0;
+    int kk = kSelK;
+    for (int shift = 56; shift >= 16; shift -= 8) {
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += NT) {
+        const uint64_t k = src[i];
+        if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xff], 1u);
+      }
+      __syncthreads();
+      if (wid == 0) {                       // 8 bins per lane: the bin where the cumulative count reaches kk
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; sum += c[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const uint32_t excl = inc - sum;
+        if (excl < (uint32_t)kk && (uint32_t)kk <= inc) {
+          uint32_t run = excl;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (run < (uint32_t)kk && (uint32_t)kk <= run + c[j]) {
+              sel_prefix = (prefix << 8) | (unsigned long long)(lane * 8 + j);
+              sel_k = kk - (int)run;
+            }
+            run += c[j];
+          }
+        }
+      }
+      __syncthreads();
+      prefix = sel_prefix;
+      kk = sel_k;
+    }
+    // keys are unique in their top 48 bits (score, anchor): exactly kSelK keys satisfy (key >> 16) <= prefix
+    for (int base = 0; base < n; base += NT) {
+      const int i = base + tid;
+      const uint64_t k = i < n ? src[i] : 0ull;
+      const bool in = i < n && (k >> 16) <= prefix;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      int pos = 0;
+      if (lane == 0 && bal) pos = atomicAdd(&cursor, __popc(bal));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (in) sB[pos + __popc(bal & ((1u << lane) - 1u))] = k;
+    }
+    __syncthreads();
+  }
+  bitonic_sort_2048(sB, tid, NT);
+  const int m = min(n_out, kSelK);
+  for (int r = tid; r < m; r += NT) orow[r] = (int)(sB[r] & 0xffff);
+}
+
 }  // namespace
+
+// Workspace layout: [header: B ints "entries of order[] that are sorted" + B ints "image needs the full-sort
+// fallback", padded to 16 B][payload: per image 2 * cap u64 keys, used when cap exceeds the shared-memory paths].
+static size_t ws_header_bytes(int B) { return (((size_t)B * 2 * sizeof(int)) + 15) & ~(size_t)15; }
 
 extern "C" size_t b200yolo_workspace_bytes(int B, int cap) {
   if (B <= 0 || cap <= 0) return 0;
-  if (cap <= kSmemKeysMax) return 16;  // shared-memory paths only; keep a non-null minimum
-  // sort: 2 key buffers of cap u64; nms: cap float4 boxes + cap flag bytes -- the larger of the two
-  return (size_t)B * ((size_t)cap + (cap + 15) / 16) * 16;
+  const size_t payload = cap <= kSmemKeysMax ? 16 : (size_t)B * ((size_t)cap + (cap + 15) / 16) * 16;
+  return ws_header_bytes(B) + payload;
+}
+
+// pass 0: the regular sort; pass 1: full sort of the images whose fallback flag is set (launched by b200yolo_nms)
+int b200_sort_launch(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
+                     int* order, void* workspace, size_t workspace_bytes, int pass, cudaStream_t s) {
+  const bool have_hdr = workspace != nullptr && workspace_bytes >= b200yolo_workspace_bytes(B, cap);
+  int* hdr = have_hdr ? reinterpret_cast<int*>(workspace) : nullptr;
+  uint64_t* payload = have_hdr ? reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + ws_header_bytes(B))
+                               : reinterpret_cast<uint64_t*>(workspace);
+  if (cap > kSmemKeysMax) B200_REQUIRE(have_hdr, B200YOLO_ERR_WORKSPACE);
+  if (pass == 1 && !have_hdr) return B200YOLO_OK;
+  if (pass == 0 && have_hdr && cap > kSelK) {
+    const int in_smem = cap <= kSmemKeysMax ? 1 : 0;
+    const size_t smem = sizeof(uint64_t) * ((size_t)kSelK + (in_smem ? (size_t)cap : 0));
+    cudaError_t e = cudaFuncSetAttribute(sort_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    sort_select_kernel<<<B, 1024, smem, s>>>(cand, cand_anchor, cand_count, cap, max_nms, order, payload, in_smem, hdr, B);
+    return b200_launch_status();
+  }
+  const int smem_keys = cap < kSmemKeysMax ? cap : kSmemKeysMax;
+  if (cap <= 1024) {
+    constexpr int NT = 256;
+    const size_t smem = 2 * sizeof(uint64_t) * (size_t)smem_keys + (NT / 32) * 256 * sizeof(uint32_t);
+    sort_topk_kernel<NT><<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, cap, max_nms, order, payload, smem_keys, hdr, B,
+                                             pass);
+  } else {
+    constexpr int NT = 1024;
+    const size_t smem = 2 * sizeof(uint64_t) * (size_t)smem_keys + (NT / 32) * 256 * sizeof(uint32_t);
+    auto kern = sort_topk_kernel<NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, cap, max_nms, order, payload, smem_keys, hdr, B, pass);
+  }
+  return b200_launch_status();
 }
 
 extern "C" int b200yolo_sort_topk(const float* cand, const int* cand_anchor, const int* cand_count, int B,
@@ -161,25 +307,8 @@ extern "C" int b200yolo_sort_topk(const float* cand, const int* cand_anchor, con
   B200_REQUIRE(cand && cand_anchor && cand_count && order, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && cap > 0 && max_nms > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(cap <= B200YOLO_MAX_SORT, B200YOLO_ERR_UNSUPPORTED);
-  if (cap > kSmemKeysMax) {
-    B200_REQUIRE(workspace, B200YOLO_ERR_NULL);
-    B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
-    B200_REQUIRE(workspace_bytes >= b200yolo_workspace_bytes(B, cap), B200YOLO_ERR_WORKSPACE);
-  }
-  const int smem_keys = cap < kSmemKeysMax ? cap : kSmemKeysMax;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (cap <= 1024) {
-    constexpr int NT = 256;
-    const size_t smem = 2 * sizeof(uint64_t) * (size_t)smem_keys + (NT / 32) * 256 * sizeof(uint32_t);
-    sort_topk_kernel<NT><<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, cap, max_nms, order,
-                                             (uint64_t*)workspace, smem_keys);
-  } else {
-    constexpr int NT = 1024;
-    const size_t smem = 2 * sizeof(uint64_t) * (size_t)smem_keys + (NT / 32) * 256 * sizeof(uint32_t);
-    auto kern = sort_topk_kernel<NT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, cap, max_nms, order, (uint64_t*)workspace, smem_keys);
-  }
-  return b200_launch_status();
+  if (workspace) B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
+  if (cap > kSmemKeysMax) B200_REQUIRE(workspace, B200YOLO_ERR_NULL);
+  return b200_sort_launch(cand, cand_anchor, cand_count, B, cap, max_nms, order, workspace, workspace_bytes, 0,
+                          (cudaStream_t)stream);
 }

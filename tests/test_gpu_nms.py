@@ -152,3 +152,35 @@ def test_oversize_images_use_workspace_paths(cuda_dev):
     kept = _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.6, max_det=500)
     assert kept == 1000
     _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.45, max_det=300, max_nms=13000)
+
+
+def test_dense_sort_prefix_and_fallback(cuda_dev):
+    """cap > 2048: K3 orders only the best 2048 entries (radix select + bitonic sort).  (a) max_det reached inside the
+    prefix: no fallback; (b) heavy overlap -- 8400 candidates in ~40 clusters per class, far fewer keeps than max_det:
+    the NMS runs out of ordered entries, flags the image, and the exact full-sort fallback produces the result;
+    (c) a batch mixing both kinds, plus an image with fewer than 2048 candidates."""
+    g = torch.Generator().manual_seed(17)
+    A, nc = 8400, 4
+
+    def clustered(n_clusters, n_live):
+        pred = torch.zeros((4 + nc, A))
+        centres = torch.rand((n_clusters, 2), generator=g) * 560 + 40
+        which = torch.randint(0, n_clusters, (A,), generator=g)
+        pred[0] = centres[which, 0] + torch.randn(A, generator=g) * 1.5
+        pred[1] = centres[which, 1] + torch.randn(A, generator=g) * 1.5
+        pred[2] = 60 + torch.rand(A, generator=g) * 4
+        pred[3] = 60 + torch.rand(A, generator=g) * 4
+        live = torch.randperm(A, generator=g)[:n_live]
+        sc = torch.rand(n_live, generator=g) * 0.98 + 0.01
+        sc[::7] = sc[0]                                                      # ties: anchor order decides
+        pred[4 + (which[live] % nc), live] = sc
+        return pred
+
+    spread = ohead.detect_inference_ref(synth.synth_head_dense(1, nc, seed=3), geometry.level_shapes(640, 640))[0]
+    batch = torch.stack([clustered(40, A), spread, clustered(25, 5000), clustered(30, 1500)])
+    kept = _check(batch, cuda_dev, conf_thres=0.001, iou_thres=0.5, max_det=300)
+    ref = onms.non_max_suppression_ref(batch, 0.001, 0.5, max_det=300)
+    assert ref[0].shape[0] < 300 and ref[1].shape[0] == 300 and ref[2].shape[0] < 300      # fallback, prefix, fallback
+    assert kept == sum(r.shape[0] for r in ref)
+    _check(batch, cuda_dev, conf_thres=0.001, iou_thres=0.5, max_det=300, agnostic=True)
+    _check(batch[:1], cuda_dev, conf_thres=0.001, iou_thres=0.9, max_det=300)             # many keeps, deep into the list
