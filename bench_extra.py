@@ -68,6 +68,28 @@ def config3(dev, B=256, nc=80, cpu_images=4):
         r["us_per_image"] = r["us_median"] / B
         out[f"nms_iou{iou}"] = r
     out["kept_mean"] = float(ws.det.count.float().mean())
+    # the production chain for this regime: class filter (scores only) + b200yolo_postprocess_dense
+    # (select-sort of the best 2048 -> DFL decode of exactly those -> windowed NMS, exact fallback)
+    cands2 = m.decode_and_filter(head, conf_thres=0.001, level_hw=lv, defer_boxes=True)
+    ws2 = m.Workspace(B, cands2.cap, 300, dev)
+
+    def cf():
+        cands2.count.zero_()
+        m.decode_and_filter(head, conf_thres=0.001, level_hw=lv, out=cands2, defer_boxes=True)
+    out["class_filter"] = timed(cf, flush=flush)
+    out["class_filter"]["algo_GBps"] = head.numel() * 4 / (out["class_filter"]["us_median"] * 1e-6) / 1e9
+    out["postprocess_dense_iou0.7"] = timed(lambda: m.postprocess_dense(cands2, ws2, head, level_hw=lv, iou_thres=0.7))
+
+    def chain():
+        cf()
+        m.postprocess_dense(cands2, ws2, head, level_hw=lv, iou_thres=0.7)
+    r = timed(chain, flush=flush)
+    r["us_per_image"] = r["us_median"] / B
+    r["algo_GBps"] = head.numel() * 4 / (r["us_median"] * 1e-6) / 1e9
+    out["dense_chain_total"] = r
+    m.nms_sorted(cands, ws, 0.7, max_det=300)
+    out["dense_chain_equals_stagewise"] = bool(torch.equal(ws2.det.count, ws.det.count) and
+                                               torch.equal(ws2.det.anchor[:, :1], ws.det.anchor[:, :1]))
     # CPU oracle on a sub-sample, scaled (flagged)
     from oracle import head as ohead
     from oracle import nms as onms

@@ -154,6 +154,19 @@ int b200yolo_postprocess_small(const b200yolo_level* levels, int n_levels, float
                                int* out_anchor, int* out_count, const uint32_t* roi_class_mask, int roi_nc,
                                int* roi_cnt, void* stream);
 
+/* ---- K2b+K3+K4 chained for the dense regime (cap > 1024; e.g. the conf = 0.001 evaluation setting) ----------
+ * Input: the survivors of b200yolo_class_filter (scores, classes, anchors; boxes not decoded yet).  One host call
+ * enqueues: select + sort of the best 2048 entries per image, DFL box decode of exactly those, windowed NMS; then,
+ * for images whose NMS ran out of ordered entries before max_det keeps (flag in the workspace header), the full
+ * sort, the full decode and the NMS again.  Same outputs, bit for bit, as b200yolo_decode_filter +
+ * b200yolo_sort_topk + b200yolo_nms; the work is proportional to what the NMS consumes.
+ * order: (B, cap) int32 scratch; workspace: b200yolo_workspace_bytes(B, cap) bytes (required). */
+int b200yolo_postprocess_dense(const b200yolo_level* levels, int n_levels, float* cand, const int* cand_anchor,
+                               const int* cand_count, int B, int cap, int max_nms, double iou_thres, float max_wh,
+                               int agnostic, int max_det, const float* scale, float* out, int* out_anchor,
+                               int* out_count, const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, int* order,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a10: ops.scale_boxes + clip_boxes on a flat (n,>=4) xyxy array (in place) --------------- */
 int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float pad_x, float pad_y,
                          float w0, float h0, void* stream);

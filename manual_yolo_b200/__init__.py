@@ -7,7 +7,8 @@ hand-written CUDA behind the C ABI of ``include/b200yolo.h`` (``libb200yolo.so``
 from . import geometry  # noqa: F401
 from .api import (Candidates, Detections, Workspace, crop_resize_rois, decode_and_filter, filter_decoded,  # noqa: F401
                   gather_slice_detections, preprocess_slices,
-                  letterbox, nms_candidates, nms_sorted, non_max_suppression, postprocess_small, preprocess,
+                  letterbox, nms_candidates, nms_sorted, non_max_suppression, postprocess_dense, postprocess_small,
+                  preprocess,
                   rois_from_detections, scale_boxes, scale_params_tensor,
                   select_rois, sort_candidates, stage_head_classes_h2d, stage_rows_h2d)
 from .pipeline import BatchStream, HostRunner, Pipeline, PipelineResult, SlicedPipeline  # noqa: F401

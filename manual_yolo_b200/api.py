@@ -411,6 +411,29 @@ def nms_sorted(cands: Candidates, ws: Workspace, iou_thres=0.45, agnostic=False,
     return ws.det
 
 
+def postprocess_dense(cands: Candidates, ws: Workspace, head, strides=(8, 16, 32), in_hw=None, level_hw=None,
+                      iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680,
+                      scale: Optional[torch.Tensor] = None, roi_mask: Optional[torch.Tensor] = None, roi_nc=0,
+                      roi_cnt: Optional[torch.Tensor] = None) -> Detections:
+    """Dense-regime chain on the survivors of ``decode_and_filter(..., defer_boxes=True)``: select-sort of the best
+    2048 entries per image -> DFL decode of exactly those -> windowed NMS (+ exact full fallback for images that
+    need more).  Bit-identical to ``decode_and_filter`` + ``sort_candidates`` + ``nms_sorted``."""
+    if not 0 <= iou_thres <= 1:
+        raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
+    B = cands.rows.shape[0]
+    if ws.max_det != max_det or ws.cap != cands.cap or ws.B != B:
+        raise ValueError("workspace does not match (B, cap, max_det)")
+    levels, n_levels, _, _, _, _, keep = _head_levels(head, strides, in_hw, level_hw)
+    rc = _lib.load().b200yolo_postprocess_dense(levels, n_levels, _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count),
+                                                B, cands.cap, int(max_nms), float(iou_thres), float(max_wh),
+                                                int(bool(agnostic)), int(max_det), _ptr(scale), _ptr(ws.det.rows),
+                                                _ptr(ws.det.anchor), _ptr(ws.det.count), _ptr(roi_mask), int(roi_nc),
+                                                _ptr(roi_cnt), _ptr(ws.order), _ptr(ws.ws), ws.ws.numel(), _stream())
+    _lib.check(rc, "postprocess_dense")
+    del keep
+    return ws.det
+
+
 def nms_candidates(cands: Candidates, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680,
                    scale: Optional[torch.Tensor] = None, ws: Optional[Workspace] = None) -> Detections:
     """K3 + K4 on K2's candidates.  ``scale``: optional (B,5) f32 {gain,pad_x,pad_y,w0,h0} -> source pixels."""

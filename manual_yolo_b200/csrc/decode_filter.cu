@@ -17,6 +17,7 @@
 // Compiled with -fmad=false: every add/mul below rounds separately, as the torch CPU ops do.
 
 #include "levels.cuh"
+#include "nms_common.cuh"
 
 namespace {
 
@@ -367,6 +368,64 @@ __global__ void __launch_bounds__(256, 6) box_decode_kernel(const Levels L, floa
   }
 }
 
+// Dense-regime form of the box decode (b200yolo_postprocess_dense): only the candidates the sort put in order
+// (the best 2048 of an image) are decoded -- the NMS consumes nothing else.  They are picked by the selection
+// threshold the sort published in the workspace header and visited in SLOT order (= runs of consecutive anchors,
+// as the class filter compacted them), so every 32-byte sector of the DFL channels is fetched once, by one warp
+// group; walking order[] instead would touch one sector per 4 useful bytes.  A CTA takes 256 slots, compacts the
+// selected ones in shared memory and decodes them 64 at a time (4 lanes per box).  pass 1 is the fallback for
+// images whose NMS ran out of ordered entries: everything is decoded.
+__global__ void __launch_bounds__(256, 6) box_decode_selected_kernel(const Levels L, float* __restrict__ cand,
+                                                                     const int* __restrict__ cand_anchor,
+                                                                     const int* __restrict__ cand_count, int cap, int B,
+                                                                     int per_image, const int* __restrict__ hdr,
+                                                                     int pass) {
+  __shared__ int sel[256];
+  __shared__ int wcnt[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, sd = tid & 3;
+  const int total = B * per_image;
+  for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    const int b = f / per_image, blk = f - b * per_image;
+    if (pass == 1 && !hdr[B + b]) continue;
+    const int n = min(cand_count[b], cap);
+    if (blk * 256 >= n) continue;
+    const unsigned long long thr48 = pass == 1 ? ~0ull
+        : (((unsigned long long)(uint32_t)hdr[3 * B + b] << 32) | (unsigned long long)(uint32_t)hdr[2 * B + b]);
+    const int s = blk * 256 + tid;
+    bool pick = false;
+    if (s < n) {
+      const float score = cand[((int64_t)b * cap + s) * 6 + 4];
+      pick = (b200::make_key(score, cand_anchor[(int64_t)b * cap + s], s) >> 16) <= thr48;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pick);
+    if (lane == 0) wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < wid) base += wcnt[w]; m += wcnt[w]; }
+    if (pick) sel[base + __popc(bal & ((1u << lane) - 1u))] = s;
+    __syncthreads();
+    for (int c0 = 0; c0 < m; c0 += 64) {
+      const int c = c0 + (tid >> 2);
+      const bool act = c < m;
+      const int slot = act ? sel[c] : 0;
+      const int a = act ? cand_anchor[(int64_t)b * cap + slot] : 0;
+      const b200::AnchorRef ar = b200::anchor_ref(L, b, a);
+      const float d = act ? b200::dfl_side(ar.p + (long long)(sd * kReg) * ar.cs, ar.cs) : 0.f;
+      const int q0 = lane & ~3;
+      const float d0 = __shfl_sync(0xffffffffu, d, q0), d1 = __shfl_sync(0xffffffffu, d, q0 + 1);
+      const float d2 = __shfl_sync(0xffffffffu, d, q0 + 2), d3 = __shfl_sync(0xffffffffu, d, q0 + 3);
+      if (act && sd == 0) {
+        const float4 bx = b200::decode_box(ar, d0, d1, d2, d3);
+        float2* row = reinterpret_cast<float2*>(cand + ((int64_t)b * cap + slot) * 6);
+        row[0] = make_float2(bx.x, bx.y);
+        row[1] = make_float2(bx.z, bx.w);
+      }
+    }
+    __syncthreads();                      // sel[] / wcnt[] are reused by the next (image, block) pair
+  }
+}
+
 // Try the vectorised path; returns -1000 if the shape is not eligible (caller falls back to the scalar kernel).
 template <bool RAW>
 static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, const uint32_t* class_mask, float* cand,
@@ -406,6 +465,23 @@ static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, cons
 }
 
 }  // namespace
+
+int b200_box_decode_sorted_launch(const b200yolo_level* levels, int n_levels, float* cand, const int* cand_anchor,
+                                  const int* cand_count, const int* order, int B, int cap, int max_nms, const int* hdr,
+                                  int pass, cudaStream_t s) {
+  (void)order; (void)max_nms;             // selection is by the published threshold, in slot order
+  Levels L;
+  const int st = b200::build_levels(levels, n_levels, L);
+  if (st != B200YOLO_OK) return st;
+  const int A = L.off[B200YOLO_MAX_LEVELS];
+  const int amax = cap < A ? cap : A;
+  const int per_image = (amax + 255) / 256;
+  const long long total = (long long)B * per_image;
+  const int wave = 6 * B200_NUM_SMS;
+  box_decode_selected_kernel<<<(unsigned)(total < wave ? total : wave), 256, 0, s>>>(L, cand, cand_anchor, cand_count, cap, B,
+                                                                                   per_image, hdr, pass);
+  return b200_launch_status();
+}
 
 static int decode_filter_impl(const b200yolo_level* levels, int n_levels, int B, int nc, float conf_thres,
                               const uint32_t* class_mask, float* cand, int* cand_anchor, int* cand_count, int cap,

@@ -222,32 +222,35 @@ __global__ void scale_boxes_kernel(float* boxes, int n, int row_stride, float ga
 
 }  // namespace
 
-extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, const int* order,
-                            int B, int cap, int max_nms, double iou_thres, float max_wh, int agnostic, int max_det,
-                            const float* scale, float* out, int* out_anchor, int* out_count,
-                            const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* workspace,
-                            size_t workspace_bytes, void* stream) {
-  B200_REQUIRE(cand && cand_anchor && cand_count && order && out && out_anchor && out_count, B200YOLO_ERR_NULL);
-  B200_REQUIRE(B > 0 && cap > 0 && max_nms > 0 && max_det > 0, B200YOLO_ERR_SHAPE);
-  B200_REQUIRE(cap <= B200YOLO_MAX_SORT && max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
-  B200_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, B200YOLO_ERR_RANGE);
-  B200_REQUIRE(roi_cnt == nullptr || (roi_class_mask != nullptr && roi_nc > 0), B200YOLO_ERR_NULL);
-  // workspace header (see sort_topk.cu): present iff the same workspace was given to b200yolo_sort_topk
-  const bool have_hdr = workspace != nullptr && workspace_bytes >= b200yolo_workspace_bytes(B, cap);
-  if (workspace) B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
-  int* hdr = have_hdr ? reinterpret_cast<int*>(workspace) : nullptr;
-  const size_t md4 = ((size_t)max_det + 3) & ~(size_t)3;
+struct NmsArgs {
+  const float* cand; const int* cand_anchor; const int* cand_count; const int* order;
+  int B, cap, max_nms; double iou_thres; float max_wh; int agnostic, max_det;
+  const float* scale; float* out; int* out_anchor; int* out_count;
+  const uint32_t* roi_class_mask; int roi_nc; int* roi_cnt;
+};
+
+static int nms_check(const NmsArgs& a) {
+  B200_REQUIRE(a.cand && a.cand_anchor && a.cand_count && a.order && a.out && a.out_anchor && a.out_count, B200YOLO_ERR_NULL);
+  B200_REQUIRE(a.B > 0 && a.cap > 0 && a.max_nms > 0 && a.max_det > 0, B200YOLO_ERR_SHAPE);
+  B200_REQUIRE(a.cap <= B200YOLO_MAX_SORT && a.max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
+  B200_REQUIRE(a.iou_thres >= 0.0 && a.iou_thres <= 1.0, B200YOLO_ERR_RANGE);
+  B200_REQUIRE(a.roi_cnt == nullptr || (a.roi_class_mask != nullptr && a.roi_nc > 0), B200YOLO_ERR_NULL);
+  return B200YOLO_OK;
+}
+
+static int nms_launch(const NmsArgs& a, int* hdr, int pass, cudaStream_t s) {
+  const size_t md4 = ((size_t)a.max_det + 3) & ~(size_t)3;
   const size_t smem = (size_t)kWindow * 16 + md4 * 16 + (size_t)kWindow * 4 + md4 * 4 + md4 * 4 + (size_t)kWindow;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (cap <= 1024) {
+  if (a.cap <= 1024) {
     constexpr int NT = 256;
     auto kern = nms_kernel<NT>;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, hdr, B, 0);
+    kern<<<a.B, NT, smem, s>>>(a.cand, a.cand_anchor, a.cand_count, a.order, a.cap, a.max_nms, a.iou_thres, a.max_wh,
+                               a.agnostic, a.max_det, a.scale, a.out, a.out_anchor, a.out_count, a.roi_class_mask,
+                               a.roi_nc, a.roi_cnt, hdr, a.B, pass);
   } else {
     constexpr int NT = 512;
     auto kern = nms_kernel<NT>;
@@ -255,21 +258,66 @@ extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                             max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, hdr, B, 0);
-    if (have_hdr && cap > 2048) {
-      // dense regime: the sort ordered only the best 2048 entries per image.  Images whose NMS ran out of them
-      // (flag raised above) are re-done exactly: full sort, then NMS again -- both launches exit at once otherwise.
-      int rc = b200_launch_status();
-      if (rc != B200YOLO_OK) return rc;
-      rc = b200_sort_launch(cand, cand_anchor, cand_count, B, cap, max_nms, const_cast<int*>(order), workspace,
-                            workspace_bytes, 1, s);
-      if (rc != B200YOLO_OK) return rc;
-      kern<<<B, NT, smem, s>>>(cand, cand_anchor, cand_count, order, cap, max_nms, iou_thres, max_wh, agnostic,
-                               max_det, scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt, hdr, B, 1);
-    }
+    kern<<<a.B, NT, smem, s>>>(a.cand, a.cand_anchor, a.cand_count, a.order, a.cap, a.max_nms, a.iou_thres, a.max_wh,
+                               a.agnostic, a.max_det, a.scale, a.out, a.out_anchor, a.out_count, a.roi_class_mask,
+                               a.roi_nc, a.roi_cnt, hdr, a.B, pass);
   }
   return b200_launch_status();
+}
+
+extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_count, const int* order,
+                            int B, int cap, int max_nms, double iou_thres, float max_wh, int agnostic, int max_det,
+                            const float* scale, float* out, int* out_anchor, int* out_count,
+                            const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  const NmsArgs a{cand, cand_anchor, cand_count, order, B, cap, max_nms, iou_thres, max_wh, agnostic, max_det,
+                  scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt};
+  int rc = nms_check(a);
+  if (rc != B200YOLO_OK) return rc;
+  // workspace header (see sort_topk.cu): present iff the same workspace was given to b200yolo_sort_topk
+  const bool have_hdr = workspace != nullptr && workspace_bytes >= b200yolo_workspace_bytes(B, cap);
+  if (workspace) B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
+  int* hdr = have_hdr ? reinterpret_cast<int*>(workspace) : nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = nms_launch(a, hdr, 0, s);
+  if (rc != B200YOLO_OK || !have_hdr || cap <= 2048) return rc;
+  // dense regime: the sort ordered only the best 2048 entries per image.  Images whose NMS ran out of them (flag
+  // raised by pass 0) are re-done exactly: full sort, then NMS again -- both launches exit at once otherwise.
+  rc = b200_sort_launch(cand, cand_anchor, cand_count, B, cap, max_nms, const_cast<int*>(order), workspace,
+                        workspace_bytes, 1, s);
+  if (rc != B200YOLO_OK) return rc;
+  return nms_launch(a, hdr, 1, s);
+}
+
+// K2b + K3 + K4 for the dense regime (cap > 1024, e.g. conf = 0.001 evaluation: every anchor is a candidate).
+// The candidates come from b200yolo_class_filter (scores and classes only).  Sorting needs no boxes, and greedy NMS
+// stops at max_det keeps, so the work is ordered to touch only what the NMS consumes: select + sort the best 2048
+// entries per image, DFL-decode exactly those, NMS over them.  An image whose NMS runs out of ordered entries is
+// flagged and re-done with the full sort and the full decode (same stream, launches exit at once otherwise).
+extern "C" int b200yolo_postprocess_dense(const b200yolo_level* levels, int n_levels, float* cand,
+                                          const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
+                                          double iou_thres, float max_wh, int agnostic, int max_det,
+                                          const float* scale, float* out, int* out_anchor, int* out_count,
+                                          const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, int* order,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  const NmsArgs a{cand, cand_anchor, cand_count, order, B, cap, max_nms, iou_thres, max_wh, agnostic, max_det,
+                  scale, out, out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt};
+  int rc = nms_check(a);
+  if (rc != B200YOLO_OK) return rc;
+  B200_REQUIRE(levels && workspace, B200YOLO_ERR_NULL);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200YOLO_ERR_ALIGN);
+  B200_REQUIRE(workspace_bytes >= b200yolo_workspace_bytes(B, cap), B200YOLO_ERR_WORKSPACE);
+  int* hdr = reinterpret_cast<int*>(workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int pass = 0; pass < (cap > 2048 ? 2 : 1); ++pass) {
+    rc = b200_sort_launch(cand, cand_anchor, cand_count, B, cap, max_nms, order, workspace, workspace_bytes, pass, s);
+    if (rc != B200YOLO_OK) return rc;
+    rc = b200_box_decode_sorted_launch(levels, n_levels, cand, cand_anchor, cand_count, order, B, cap, max_nms, hdr, pass, s);
+    if (rc != B200YOLO_OK) return rc;
+    rc = nms_launch(a, hdr, pass, s);
+    if (rc != B200YOLO_OK) return rc;
+  }
+  return B200YOLO_OK;
 }
 
 extern "C" int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float pad_x, float pad_y,

@@ -9,6 +9,11 @@
 int b200_sort_launch(const float* cand, const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
                      int* order, void* workspace, size_t workspace_bytes, int pass, cudaStream_t s);
 
+// decode_filter.cu: DFL box decode of the ordered candidates only (pass 0) / of everything for flagged images (pass 1)
+int b200_box_decode_sorted_launch(const b200yolo_level* levels, int n_levels, float* cand, const int* cand_anchor,
+                                  const int* cand_count, const int* order, int B, int cap, int max_nms, const int* hdr,
+                                  int pass, cudaStream_t s);
+
 namespace b200 {
 
 // Sort key: ascending key order == score descending, anchor ascending on ties (the reference's stable

@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
   if (pass == 1 && !(hdr && hdr[B + b])) return;           // fallback launch: only the images the NMS flagged
   const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
   const int n_out = min(max(n, 0), max_nms);
-  if (hdr && tid == 0) { hdr[b] = n_out; if (pass == 0) hdr[B + b] = 0; }   // every entry sorted; no fallback pending
+  if (hdr && tid == 0) {   // every entry sorted, no fallback pending, threshold = "every key"
+    hdr[b] = n_out; hdr[2 * B + b] = -1; hdr[3 * B + b] = -1;
+    if (pass == 0) hdr[B + b] = 0;
+  }
   if (n <= 0) return;
   const float* crow = cand + (int64_t)b * cap * 6;
   const int* arow = cand_anchor + (int64_t)b * cap;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
   const int n_out = min(max(n, 0), max_nms);
-  if (tid == 0) { hdr[b] = min(n_out, kSelK); hdr[B + b] = 0; }
+  if (tid == 0) { hdr[b] = min(n_out, kSelK); hdr[B + b] = 0; hdr[2 * B + b] = -1; hdr[3 * B + b] = -1; }
   if (n <= 0) return;
   if (!keys_in_smem) src = ws + (int64_t)b * 2 * cap;
   const float* crow = cand + (int64_t)b * cap * 6;
@@ -237,7 +240,9 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
       prefix = sel_prefix;
       kk = sel_k;
     }
-    // keys are unique in their top 48 bits (score, anchor): exactly kSelK keys satisfy (key >> 16) <= prefix
+    // keys are unique in their top 48 bits (score, anchor): exactly kSelK keys satisfy (key >> 16) <= prefix.
+    // The threshold goes to the header: the box decode of b200yolo_postprocess_dense selects by it, in slot order.
+    if (tid == 0) { hdr[2 * B + b] = (int)(uint32_t)(prefix & 0xffffffffu); hdr[3 * B + b] = (int)(uint32_t)(prefix >> 32); }
     for (int base = 0; base < n; base += NT) {
       const int i = base + tid;
       const uint64_t k = i < n ? src[i] : 0ull;
@@ -257,9 +262,10 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
 
 }  // namespace
 
-// Workspace layout: [header: B ints "entries of order[] that are sorted" + B ints "image needs the full-sort
-// fallback", padded to 16 B][payload: per image 2 * cap u64 keys, used when cap exceeds the shared-memory paths].
-static size_t ws_header_bytes(int B) { return (((size_t)B * 2 * sizeof(int)) + 15) & ~(size_t)15; }
+// Workspace layout: [header: 4 x B ints -- entries of order[] that are sorted | image needs the full-sort fallback |
+// low 32 / high 16 bits of the selection threshold (key >> 16 of the last ordered entry; all ones = every key) --
+// padded to 16 B][payload: per image 2 * cap u64 keys, used when cap exceeds the shared-memory paths].
+static size_t ws_header_bytes(int B) { return (((size_t)B * 4 * sizeof(int)) + 15) & ~(size_t)15; }
 
 extern "C" size_t b200yolo_workspace_bytes(int B, int cap) {
   if (B <= 0 || cap <= 0) return 0;

@@ -146,15 +146,16 @@ class Pipeline:
                                         max_wh=self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
                                         roi_cnt=self.roi_cnt)
         else:
+            # general / dense regime: class filter, then ONE host call for select-sort -> decode of the ordered
+            # prefix -> windowed NMS (+ exact fallback)
             t("decode_filter")
             api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
-                                  cap=self.cap, out=self.cands)
-            t("sort_topk")
-            api.sort_candidates(self.cands, self.max_nms, self.ws)
-            t("nms")
-            det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms,
-                                 self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
-                                 roi_cnt=self.roi_cnt)
+                                  cap=self.cap, out=self.cands, defer_boxes=True)
+            t("postprocess_dense")
+            det = api.postprocess_dense(self.cands, self.ws, head, self.strides, level_hw=self.level_hw,
+                                        iou_thres=self.iou, agnostic=self.agnostic, max_det=self.max_det,
+                                        max_nms=self.max_nms, max_wh=self.max_wh, scale=self.scale,
+                                        roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
         t("roi_crop_resize")
         ro = api.rois_from_detections(self._roi_frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
@@ -227,7 +228,7 @@ class Pipeline:
     def launches_per_step(self):
         """Kernels of this package launched per step: letterbox, class filter, [fused post-processing | box
         decode, sort, nms], ROI crops, large-ROI pass."""
-        return 5 if self.fused else 7
+        return 5 if self.fused else (10 if self.cap > 2048 else 7)
 
     def check_overflow(self):
         """Raise if any image of the last step had more candidates than ``cap`` (one D2H of the counts).

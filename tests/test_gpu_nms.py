@@ -184,3 +184,28 @@ def test_dense_sort_prefix_and_fallback(cuda_dev):
     assert kept == sum(r.shape[0] for r in ref)
     _check(batch, cuda_dev, conf_thres=0.001, iou_thres=0.5, max_det=300, agnostic=True)
     _check(batch[:1], cuda_dev, conf_thres=0.001, iou_thres=0.9, max_det=300)             # many keeps, deep into the list
+
+
+def test_postprocess_dense_equals_stagewise_chain(cuda_dev):
+    """b200yolo_postprocess_dense (class filter -> select-sort -> decode of the ordered prefix -> windowed NMS, with
+    the exact fallback) must be bit-identical to decode_and_filter + sort_candidates + nms_sorted and to the oracle,
+    for a spread dense head (max_det reached inside the prefix) and for a low max_det / high max_det mix."""
+    lv = geometry.level_shapes(640, 640)
+    head = synth.synth_head_dense(3, 80, seed=5)
+    hd = head.to(cuda_dev)
+    pred = ohead.detect_inference_ref(head, lv)
+    for conf, iou, max_det in ((0.001, 0.7, 300), (0.001, 0.45, 3000), (0.05, 0.6, 50)):
+        ref_out, ref_idx = onms.non_max_suppression_ref(pred, conf, iou, max_det=max_det, return_idxs=True)
+        stage = m.nms_candidates(m.decode_and_filter(hd, conf_thres=conf, level_hw=lv), iou, max_det=max_det)
+        s_rows, s_anchor, s_count = stage.rows.clone(), stage.anchor.clone(), stage.count.clone()
+        cands = m.decode_and_filter(hd, conf_thres=conf, level_hw=lv, defer_boxes=True)
+        ws = m.Workspace(3, cands.cap, max_det, cuda_dev)
+        det = m.postprocess_dense(cands, ws, hd, level_hw=lv, iou_thres=iou, max_det=max_det)
+        assert torch.equal(det.count, s_count)
+        for b in range(3):
+            k = int(s_count[b])
+            assert k == ref_out[b].shape[0]
+            assert torch.equal(det.anchor[b, :k], s_anchor[b, :k]) and torch.equal(det.rows[b, :k], s_rows[b, :k])
+            assert torch.equal(det.anchor[b, :k].cpu().long(), ref_idx[b])
+            assert torch.equal(det.rows[b, :k].cpu()[:, 5], ref_out[b][:, 5])
+            assert (det.rows[b, :k].cpu()[:, :5] - ref_out[b][:, :5]).abs().max().item() <= 1e-4
