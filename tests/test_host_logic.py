@@ -144,3 +144,38 @@ def test_slice_boxes_layout():
     import pytest
     with pytest.raises(ValueError):
         geometry.slice_boxes(100, 100, 10, 10, 1.0, 1.0)
+
+
+def test_tracker_handoff_and_jsonl_emission(tmp_path):
+    """N2/N4 host formats: sv.Detections-style arrays with create_clean_detections' cleaning rules
+    (detect.py:253-310) and append-only JSONL with the reference's per-frame object (detect.py:590-598, 679-683)."""
+    import json
+    import numpy as np
+    import torch
+    from manual_yolo_b200 import handoff
+    rows = torch.zeros((3, 4, 6))
+    rows[0, 0] = torch.tensor([10.9, 20.2, 30.7, 40.99, 0.87654, 6.0])
+    rows[0, 1] = torch.tensor([1.0, 2.0, 3.0, 4.0, float("nan"), float("nan")])
+    rows[2, 0] = torch.tensor([5.5, 6.5, 7.5, 8.5, 0.5, 11.0])
+    count = torch.tensor([2, 0, 1])
+    arr = handoff.to_tracker_arrays(rows, count, tracker_ids=[[3, None], [], [float("nan")]])
+    assert [a["xyxy"].shape for a in arr] == [(2, 4), (0, 4), (1, 4)]
+    assert arr[0]["xyxy"].dtype == np.float32 and arr[0]["class_id"].dtype == np.int32
+    assert arr[0]["class_id"].tolist() == [6, 0] and arr[0]["confidence"].tolist() == [np.float32(0.87654), 0.0]
+    assert arr[0]["tracker_id"].tolist() == [3, -1] and arr[2]["tracker_id"].tolist() == [-1]
+    assert handoff.to_tracker_arrays(rows, count)[0]["tracker_id"] is None
+    rows[0, 1, 4:] = torch.tensor([0.25, 3.0])
+    objs = handoff.frame_objects(rows, count, names={6: "card1_rank"}, frame_offset=100, timestamp=1.5)
+    assert objs[0]["frame"] == 100 and objs[1]["detections"] == [] and objs[2]["frame"] == 102
+    d0 = objs[0]["detections"][0]
+    assert d0 == {"frame": 100, "tracker_id": -1, "class_id": 6, "class_name": "card1_rank", "bbox": [10, 20, 30, 40],
+                  "conf": 0.877, "ocr_text": ""}
+    assert objs[0]["detections"][1]["class_name"] == "class3"
+    p = tmp_path / "det.jsonl"
+    with handoff.JsonlWriter(str(p)) as w:
+        w.write_batch(objs)
+        first = w.bytes
+        w.write_batch(handoff.frame_objects(rows, count, frame_offset=103, timestamp=2.5))
+        assert w.frames == 6 and w.bytes < 2.2 * first           # appended, not re-dumped
+    back = handoff.load_jsonl_as_reference_list(str(p))
+    assert [o["frame"] for o in back] == [100, 101, 102, 103, 104, 105] and back[0] == json.loads(json.dumps(objs[0]))
