@@ -146,17 +146,21 @@ def config_n3(dev, F=16):
 
 
 def config1(dev):
+    """BASELINE configs[0]: one 1600x900 frame (test2.png shape), imgsz 640, conf 0.25, iou 0.45.  cap=1024 is the
+    fused sparse-regime path (what this confidence threshold calls for); cap=None the general path."""
     out = {}
     frame = synth.synth_frames(1, 900, 1600, seed=0)
     for auto in (False, True):
-        pipe = m.Pipeline(1, (900, 1600), 64, imgsz=640, auto=auto, conf=0.25, iou=0.45, device=dev)
-        head, _ = synth.synth_head_from_labels(1, 64, in_hw=pipe.in_hw, src_hw=(900, 1600), seed=0)
-        f, h = frame.to(dev), head.to(dev)
-        eager = timed(lambda: pipe(f, h), iters=20)
-        pipe.capture(f, h)
-        graph = timed(lambda: pipe.replay(), iters=20)
-        out[f"auto={auto}"] = {"in_hw": list(pipe.in_hw), "anchors": pipe.A, "eager": eager, "cuda_graph": graph,
-                               "detections": int(pipe.ws.det.count[0])}
+        for cap in (1024, None):
+            pipe = m.Pipeline(1, (900, 1600), 64, imgsz=640, auto=auto, conf=0.25, iou=0.45, device=dev, cap=cap)
+            head, _ = synth.synth_head_from_labels(1, 64, in_hw=pipe.in_hw, src_hw=(900, 1600), seed=0)
+            f, h = frame.to(dev), head.to(dev)
+            eager = timed(lambda: pipe(f, h), iters=20)
+            pipe.capture(f, h)
+            graph = timed(lambda: pipe.replay(), iters=20)
+            key = f"auto={auto}" + ("" if cap else ",general_path")
+            out[key] = {"in_hw": list(pipe.in_hw), "anchors": pipe.A, "cap": pipe.cap, "fused": pipe.fused, "eager": eager,
+                        "cuda_graph": graph, "detections": int(pipe.ws.det.count[0])}
     return out
 
 

@@ -195,6 +195,18 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
   const int* arow = cand_anchor + (int64_t)b * cap;
   int* orow = order + (int64_t)b * cap;
 
+  if (n <= kEnumMax) {
+    // sparse image inside a dense-capable launch: enumeration sort (rank = number of smaller keys; keys are unique)
+    for (int i = tid; i < n; i += NT) sB[i] = make_key(crow[i * 6 + 4], arow[i], i);
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+      const uint64_t k = sB[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (sB[j] < k);
+      if (rank < n_out) orow[rank] = (int)(k & 0xffff);
+    }
+    return;
+  }
   if (n <= kSelK) {
     // everything fits the bitonic network: pad with the largest key
     for (int i = tid; i < kSelK; i += NT) sB[i] = i < n ? make_key(crow[i * 6 + 4], arow[i], i) : ~0ull;
