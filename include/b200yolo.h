@@ -214,6 +214,15 @@ int b200yolo_gather_slice_detections(const float* det, const int* det_count, int
                                      int max_det, const int* slice_xy, float* cand, int* cand_anchor,
                                      int* cand_count, int cap, void* stream);
 
+/* ---- N2: tracker association costs -------------------------------------------------------------------------
+ * The reference hands each frame's detections to supervision ByteTrack (detect.py:557); its association step is
+ * cost = 1 - box_iou_batch(tracks, detections), optionally fused with the detection scores
+ * (1 - (1 - cost) * score), then a linear assignment on the host.  tracks: (B, T, 4) float32 xyxy (16-byte
+ * aligned) + track_count (B); det / det_count: the padded output of b200yolo_nms.  cost: (B, T, max_det)
+ * float32; entries outside (track_count[b], det_count[b]) are set to pad_cost. */
+int b200yolo_iou_cost_matrix(const float* tracks, const int* track_count, const float* det, const int* det_count,
+                             int B, int T, int max_det, int fuse_score, float pad_cost, float* cost, void* stream);
+
 size_t b200yolo_workspace_bytes(int B, int cap);
 
 /* ---- host -> device staging of the source rows K1 references ------------------------------------

@@ -575,3 +575,28 @@ def select_rois(det: Detections, classes, nc, roi_cap, out=None):
                                           _stream())
     _lib.check(rc, "select_rois")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: tracker association costs
+# ------------------------------------------------------------------------------------------------
+def iou_cost_matrix(tracks_xyxy: torch.Tensor, track_count: torch.Tensor, det: Detections, fuse_score=False,
+                    pad_cost=1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ByteTrack association costs for a batch of frames / streams (``detect.py:557`` ->
+    supervision ``iou_distance`` [+ ``fuse_score``]): ``tracks_xyxy`` (B,T,4) fp32 predicted track boxes,
+    ``track_count`` (B,) int32, ``det`` the padded NMS output.  Returns (B,T,max_det) fp32 costs ``1 - iou``
+    (``1 - iou * score`` when fused); padding entries hold ``pad_cost``.  The linear assignment stays on the host
+    (``handoff.associate``)."""
+    _require_cuda(tracks_xyxy, "tracks_xyxy", torch.float32)
+    _require_cuda(track_count, "track_count", torch.int32)
+    tracks_xyxy = tracks_xyxy.contiguous()
+    if tracks_xyxy.dim() != 3 or tracks_xyxy.shape[2] != 4 or tracks_xyxy.shape[0] != det.rows.shape[0]:
+        raise ValueError("tracks_xyxy must be (B,T,4) with the same B as det")
+    B, T, _ = tracks_xyxy.shape
+    max_det = det.rows.shape[1]
+    if out is None:
+        out = torch.empty((B, T, max_det), dtype=torch.float32, device=tracks_xyxy.device)
+    rc = _lib.load().b200yolo_iou_cost_matrix(_ptr(tracks_xyxy), _ptr(track_count), _ptr(det.rows), _ptr(det.count), B, T,
+                                              max_det, int(bool(fuse_score)), float(pad_cost), _ptr(out), _stream())
+    _lib.check(rc, "iou_cost_matrix")
+    return out

@@ -102,3 +102,22 @@ def load_jsonl_as_reference_list(path: str) -> List[dict]:
     """The list the reference's ``json.dump(all_detections, ...)`` holds, rebuilt from the JSONL file."""
     with open(path, encoding="utf-8") as f:
         return [json.loads(line) for line in f if line.strip()]
+
+
+def associate(cost: np.ndarray, thresh: float):
+    """Linear assignment of tracks (rows) to detections (columns) on a cost matrix from ``api.iou_cost_matrix``
+    (already cut to the valid (n_tracks, n_dets) block): minimum-cost matching, pairs costlier than ``thresh`` are
+    left unmatched -- the role of ``matching.linear_assignment(cost, thresh)`` in supervision's ByteTrack (which uses
+    ``lap.lapjv(cost_limit=thresh)``; scipy's solver is what this image has).
+    Returns (matches (k,2) int, unmatched_tracks, unmatched_dets)."""
+    from scipy.optimize import linear_sum_assignment
+    cost = np.asarray(cost, np.float64)
+    if cost.size == 0:
+        return np.zeros((0, 2), int), list(range(cost.shape[0])), list(range(cost.shape[1]))
+    safe = np.where(np.isfinite(cost), cost, 1e6)
+    r, c = linear_sum_assignment(safe)
+    ok = safe[r, c] <= thresh
+    matches = np.stack([r[ok], c[ok]], 1).astype(int)
+    ut = sorted(set(range(cost.shape[0])) - set(matches[:, 0].tolist()))
+    ud = sorted(set(range(cost.shape[1])) - set(matches[:, 1].tolist()))
+    return matches, ut, ud

@@ -30,4 +30,4 @@ Pinning status
   are checked bit-for-bit against the real cv2 / torchvision leaves instead.
 """
 
-from . import boxes, head, letterbox, nms, roi  # noqa: F401
+from . import assoc, boxes, head, letterbox, nms, roi  # noqa: F401
