@@ -152,6 +152,15 @@ def test_oversize_images_use_workspace_paths(cuda_dev):
     kept = _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.6, max_det=500)
     assert kept == 1000
     _check(pred, cuda_dev, conf_thres=0.05, iou_thres=0.45, max_det=300, max_nms=13000)
+    # heavy overlap at this size: few keeps -> the NMS exhausts the ordered prefix -> exact fallback, whose full sort
+    # runs in the workspace (keys do not fit shared memory)
+    centres = torch.rand((30, 2), generator=g) * 800 + 50
+    which = torch.randint(0, 30, (A,), generator=g)
+    pred[0, 0] = centres[which, 0] + torch.randn(A, generator=g)
+    pred[0, 1] = centres[which, 1] + torch.randn(A, generator=g)
+    pred[0, 2:4] = 50.0
+    kept = _check(pred[:1], cuda_dev, conf_thres=0.05, iou_thres=0.5, max_det=300)
+    assert kept < 300
 
 
 def test_dense_sort_prefix_and_fallback(cuda_dev):
