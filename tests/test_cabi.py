@@ -74,3 +74,23 @@ def test_cpu_tensors_rejected():
         m.non_max_suppression(torch.zeros((1, 10, 20)))
     with pytest.raises(NotImplementedError):
         m.non_max_suppression(torch.zeros((1, 10, 20)), rotated=True)
+
+
+def test_header_is_valid_c_and_matches_bindings(tmp_path):
+    """include/b200yolo.h must compile as plain C (it is the drop-in boundary for non-Python hosts) and every function it
+    declares must be bound in _lib.SIGNATURES with the same number of parameters."""
+    import re
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b200yolo.h")
+    src = tmp_path / "use.c"
+    src.write_text('#include "b200yolo.h"\nint (*entry)(void) = b200yolo_version;\nint main(void) { return entry == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.dirname(hdr), str(src)],
+                   check=True)
+    text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    decls = re.findall(r"\b(b200yolo_\w+)\s*\(([^;{}]*?)\)\s*;", text)
+    names = {n for n, _ in decls}
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    for name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
