@@ -19,7 +19,7 @@
 // window is first tested against them.  Inside a window boxes are processed in chunks of 64 (sorted order): (A) the
 // 64x64 intra-chunk IoU bitmask is built in parallel (4 pairs per thread, rows merged with warp shuffles), (B) one
 // thread resolves the chunk serially over the mask words (ffs over the alive bits), (C) the chunk's kept boxes
-// are applied to every later box of the window in parallel.  ~30 KB of shared memory per CTA: several images per
+// are applied to every later box of the window in parallel.  ~19 KB of shared memory per CTA: several images per
 // SM, so a batch of 256 images is one wave.  Compiled with -fmad=false.
 
 #include "nms_common.cuh"
@@ -32,7 +32,7 @@ using b200::may_overlap;
 using b200::scale_clip;
 
 constexpr int kChunk = 64;
-constexpr int kWindow = 1024;          // sorted boxes resident at a time
+constexpr int kWindow = 512;           // sorted boxes resident at a time
 
 template <int NT>
 __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand, const int* __restrict__ cand_anchor,
