@@ -121,3 +121,71 @@ def associate(cost: np.ndarray, thresh: float):
     ut = sorted(set(range(cost.shape[0])) - set(matches[:, 0].tolist()))
     ud = sorted(set(range(cost.shape[1])) - set(matches[:, 1].tolist()))
     return matches, ut, ud
+
+
+# ---- N1: rank-classifier hand-off (detect.py:115-139 classify_card_rank, :60-98 normalize_rank_text) --------------
+VALID_CARD_RANKS = frozenset({"A", "K", "Q", "J", "10", "9", "8", "7", "6", "5", "4", "3", "2"})   # detect.py:36
+_LOOKALIKE = {"O": "0", "I": "1", "S": "5", "Z": "2", "B": "8", "T": "10"}                          # detect.py:37
+_NUMERIC_RANKS = frozenset(str(v) for v in range(2, 11))
+
+
+def normalize_rank_text(text: str) -> str:
+    """Classifier / OCR text -> one of A,K,Q,J,10,9..2, or "" (behaviour of ``detect.py:60-98``, pinned by
+    ``tests/golden/rank_text_golden.json``, which was produced by executing the reference's own function)."""
+    if not text:
+        return ""
+    t = text.strip().upper()
+    if len(t) == 1:
+        t = _LOOKALIKE.get(t, t)                       # single look-alike letters first
+    t = t.replace(" ", "").replace("|", "1").replace("O", "0")
+    if t == "T":
+        t = "10"
+    if t in ("A", "K", "Q", "J"):
+        return t
+    if t.isdigit():
+        if t == "0":                                   # a lone zero is a ten that lost its one
+            t = "10"
+        if t in _NUMERIC_RANKS:
+            return t
+    if len(t) == 1 and t in _LOOKALIKE:                # last chance for a single look-alike
+        m = "10" if _LOOKALIKE[t] == "0" else _LOOKALIKE[t]
+        if m in _NUMERIC_RANKS:
+            return m
+    return ""
+
+
+def rank_text_from_top1(pred_name: str, top1conf: float, det_class_name: str = "") -> str:
+    """``classify_card_rank``'s decision (``detect.py:115-139``): accept the classifier's top-1 when its confidence
+    reaches 0.20 for turn/river cards and 0.40 otherwise; cleaned rank if valid, else the upper-cased name."""
+    low = det_class_name.lower()
+    threshold = 0.20 if ("turn" in low or "river" in low) else 0.40
+    if top1conf >= threshold:
+        cleaned = normalize_rank_text(pred_name)
+        return cleaned if cleaned in VALID_CARD_RANKS else pred_name.upper()
+    return ""
+
+
+def classify_rank_rois(result, forward_logits, rank_names: dict, det_names: Optional[dict] = None) -> List[dict]:
+    """Batched form of the reference's per-crop loop (``detect.py:580-588`` -> ``:121-131``): ONE forward of the
+    rank classifier over the K5 batch of a step (``result``: a ``PipelineResult``), one device->host read of
+    (top1, top1conf), then the reference's thresholds and text clean-up.  ``forward_logits``: callable mapping the
+    (n,3,64,64) fp32 ROI tensor to (n,13) logits (the YOLOv8n-cls network stays torch).  Returns one dict per valid
+    ROI: frame, det (row in that frame's detections), class_id, top1, top1conf, text."""
+    import torch
+    n = int(result.roi_count)
+    if n == 0:
+        return []
+    probs = forward_logits(result.rois[:n]).softmax(1)
+    conf, top1 = probs.max(1)
+    conf, top1 = conf.cpu().tolist(), top1.cpu().tolist()
+    frames, dets, valid = result.roi_batch[:n].cpu().tolist(), result.roi_det[:n].cpu().tolist(), result.roi_valid[:n].cpu().tolist()
+    cls = result.det.rows[result.roi_batch[:n].long(), result.roi_det[:n].long(), 5].cpu().tolist()
+    out = []
+    for i in range(n):
+        if valid[i] <= 0:                               # safe_crop returned None: classify_card_rank returns ""
+            continue
+        cid = int(cls[i])
+        dname = det_names.get(cid, f"class{cid}") if det_names else f"class{cid}"
+        out.append({"frame": frames[i], "det": dets[i], "class_id": cid, "top1": top1[i], "top1conf": conf[i],
+                    "text": rank_text_from_top1(rank_names.get(top1[i], ""), conf[i], dname)})
+    return out

@@ -136,3 +136,44 @@ def test_select_rois_order_and_count(cuda_dev):
     # capacity clamp
     _, _, _, rc2 = m.select_rois(det, classes, nc, roi_cap=5)
     assert int(rc2.cpu()) == 5
+
+
+def test_classifier_chain_batched(cuda_dev, golden_dir):
+    """N1: the per-crop loop of detect.py:580-588 -> :121-131 as ONE K5 launch + ONE classifier forward +
+    the reference's thresholds / text rules: 67 validation crops pasted into two frames, detected as rank-class
+    boxes, cropped from the detections on the device, classified; 63 of 67 texts equal the folder label."""
+    from manual_yolo_b200 import handoff
+    z, crops = _kat_crops(golden_dir)
+    names = dict(enumerate(["10", "2", "3", "4", "5", "6", "7", "8", "9", "A", "J", "K", "Q"]))   # rank_classifier/valid/* sorted
+    B, H, W, max_det = 2, 512, 1024, 300
+    canvas = np.random.default_rng(0).integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    rows = torch.zeros((B, max_det, 6))
+    count = [0, 0]
+    x, y, rowh, f = 4, 4, 0, 0
+    where = []
+    for i, c in enumerate(crops):
+        h, w = c.shape[:2]
+        if x + w + 4 > W:
+            x, y, rowh = 4, y + rowh + 4, 0
+        if y + h + 4 > H:
+            f, x, y, rowh = f + 1, 4, 4, 0
+        canvas[f, y:y + h, x:x + w] = c
+        rows[f, count[f]] = torch.tensor([x + 0.3, y + 0.6, x + w + 0.4, y + h + 0.9, 0.9, 6.0 if i % 2 else 37.0])   # card1_rank / turn_rank ids
+        where.append((f, count[f]))
+        count[f] += 1
+        x, rowh = x + w + 4, max(rowh, h)
+    det = m.Detections(rows.to(cuda_dev), torch.zeros((B, max_det), dtype=torch.int32, device=cuda_dev),
+                       torch.tensor(count, dtype=torch.int32, device=cuda_dev))
+    mask = m.api._class_mask(m.pipeline.RANK_CLASS_IDS, 64, cuda_dev)
+    roi_cnt = torch.tensor(count, dtype=torch.int32, device=cuda_dev)
+    ro = m.rois_from_detections(torch.from_numpy(canvas).to(cuda_dev), det, roi_cnt, mask, 64, roi_cap=128, pad=0)
+    res = m.PipelineResult(None, det, None, *ro)
+    assert int(res.roi_count) == len(crops)
+    sd = ocls.state_dict_from_npz(z, device=cuda_dev)
+    out = handoff.classify_rank_rois(res, lambda t: ocls.forward_logits(sd, t), names,
+                                     det_names={6: "card1_rank", 37: "turn_rank"})
+    assert [(o["frame"], o["det"]) for o in out] == where
+    labels = z["labels"].tolist()
+    assert sum(o["top1"] == l for o, l in zip(out, labels)) == 63                      # the reference's known answer
+    texts_ok = sum(o["text"] == names[l] for o, l in zip(out, labels))
+    assert texts_ok >= 60 and all(o["text"] in handoff.VALID_CARD_RANKS or o["text"] == "" for o in out)

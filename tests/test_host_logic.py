@@ -179,3 +179,28 @@ def test_tracker_handoff_and_jsonl_emission(tmp_path):
         assert w.frames == 6 and w.bytes < 2.2 * first           # appended, not re-dumped
     back = handoff.load_jsonl_as_reference_list(str(p))
     assert [o["frame"] for o in back] == [100, 101, 102, 103, 104, 105] and back[0] == json.loads(json.dumps(objs[0]))
+
+
+def test_reference_helpers_golden(golden_dir):
+    """Golden vectors produced by EXECUTING the reference's own helpers (tests/golden/make_rank_text_golden.py cuts
+    normalize_rank_text and safe_crop out of /root/reference/detect.py and runs them unmodified): they pin the
+    classifier hand-off text rules and the crop geometry the oracle (and through it K5) follows."""
+    import json
+    import os
+    import numpy as np
+    from manual_yolo_b200 import handoff
+    from oracle import boxes as oboxes
+    g = json.load(open(os.path.join(golden_dir, "rank_text_golden.json")))
+    assert sorted(handoff.VALID_CARD_RANKS) == g["valid_card_ranks"]
+    for text, want in g["normalize_rank_text"]:
+        assert handoff.normalize_rank_text(text) == want, (text, want)
+    H, W = g["frame_hw"]
+    frame = np.zeros((H, W, 3), np.uint8)
+    for x1, y1, x2, y2, pad, shape in g["safe_crop_shapes"]:
+        crop = oboxes.safe_crop_ref(frame, x1, y1, x2, y2, pad=pad)
+        assert (None if crop is None else list(crop.shape[:2])) == shape, (x1, y1, x2, y2, pad)
+    # classify_card_rank thresholds (detect.py:127-131)
+    assert handoff.rank_text_from_top1("k", 0.41, "card1_rank") == "K"
+    assert handoff.rank_text_from_top1("k", 0.39, "card1_rank") == ""
+    assert handoff.rank_text_from_top1("10", 0.21, "turn_rank") == "10" and handoff.rank_text_from_top1("10", 0.19, "river_rank") == ""
+    assert handoff.rank_text_from_top1("joker", 0.9, "flop1_rank") == "JOKER"
