@@ -189,3 +189,24 @@ def classify_rank_rois(result, forward_logits, rank_names: dict, det_names: Opti
         out.append({"frame": frames[i], "det": dets[i], "class_id": cid, "top1": top1[i], "top1conf": conf[i],
                     "text": rank_text_from_top1(rank_names.get(top1[i], ""), conf[i], dname)})
     return out
+
+
+def to_pipe_records(det_rows, det_count, names: Optional[dict], image_shape) -> List[List[dict]]:
+    """Per-frame detection dicts as ``pipe.py``'s ``parse_ultralytics_results`` builds them (``pipe.py:100-134``):
+    ``int()``-truncated coordinates, then ``x1,y1`` clamped at 0 and ``x2,y2`` at ``w-1`` / ``h-1``; ``conf`` float,
+    ``class_id`` int, ``class_name`` from ``names`` (``class<id>`` when missing).  Pinned by
+    ``tests/golden/pipe_records_golden.json`` (produced by executing the reference's function)."""
+    rows = det_rows.tolist() if hasattr(det_rows, "tolist") else det_rows
+    counts = det_count.tolist() if hasattr(det_count, "tolist") else det_count
+    h, w = int(image_shape[0]), int(image_shape[1])
+    out = []
+    for b, n in enumerate(counts):
+        recs = []
+        for i in range(n):
+            x1, y1, x2, y2, conf, cls = rows[b][i]
+            cid = int(cls)
+            recs.append({"x1": max(0, int(x1)), "y1": max(0, int(y1)), "x2": min(w - 1, int(x2)), "y2": min(h - 1, int(y2)),
+                         "conf": float(conf), "class_id": cid,
+                         "class_name": names.get(cid, f"class{cid}") if names else f"class{cid}"})
+        out.append(recs)
+    return out

@@ -204,3 +204,21 @@ def test_reference_helpers_golden(golden_dir):
     assert handoff.rank_text_from_top1("k", 0.39, "card1_rank") == ""
     assert handoff.rank_text_from_top1("10", 0.21, "turn_rank") == "10" and handoff.rank_text_from_top1("10", 0.19, "river_rank") == ""
     assert handoff.rank_text_from_top1("joker", 0.9, "flop1_rank") == "JOKER"
+
+
+def test_pipe_records_golden(golden_dir):
+    """Row a11 consumer: handoff.to_pipe_records == the reference's own parse_ultralytics_results (pipe.py:100-134),
+    whose outputs on seeded boxes were recorded by executing it (tests/golden/make_pipe_records_golden.py)."""
+    import json
+    import os
+    import torch
+    from manual_yolo_b200 import handoff
+    g = json.load(open(os.path.join(golden_dir, "pipe_records_golden.json")))
+    names = {int(k): v for k, v in g["names"].items()}
+    for case in g["cases"]:
+        n = len(case["rows"])
+        rows = torch.zeros((1, max(n, 1), 6))
+        if n:
+            rows[0, :n] = torch.tensor(case["rows"], dtype=torch.float32)
+        got = handoff.to_pipe_records(rows, torch.tensor([n]), names, case["image_shape"])[0]
+        assert got == case["records"]
