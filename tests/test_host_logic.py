@@ -222,3 +222,35 @@ def test_pipe_records_golden(golden_dir):
             rows[0, :n] = torch.tensor(case["rows"], dtype=torch.float32)
         got = handoff.to_pipe_records(rows, torch.tensor([n]), names, case["image_shape"])[0]
         assert got == case["records"]
+
+
+def test_clean_detections_golden(golden_dir):
+    """Tracker hand-off cleaning rules == the reference's own create_clean_detections (detect.py:253-310), whose
+    outputs were recorded by executing it with a stand-in for sv.Detections (make_clean_detections_golden.py).
+    Cases expressible in the padded device layout (NaN class / confidence, None / NaN tracker ids, empty frame)."""
+    import json
+    import os
+    import numpy as np
+    import torch
+    from manual_yolo_b200 import handoff
+    g = json.load(open(os.path.join(golden_dir, "clean_detections_golden.json")))
+
+    def f(v):
+        return float("nan") if v in ("nan", None) else float(v)
+    for case in g["cases"]:
+        cin = case["in"]
+        n = len(cin["xyxy"])
+        if cin["class_id"] is None or cin["confidence"] is None:
+            continue                                   # "argument omitted" has no counterpart: the device rows always carry both
+        rows = torch.zeros((1, max(n, 1), 6))
+        for i in range(n):
+            rows[0, i] = torch.tensor(cin["xyxy"][i] + [f(cin["confidence"][i]), f(cin["class_id"][i])])
+        tid = None if cin["tracker_id"] is None else [[None if v is None else (float("nan") if v == "nan" else v) for v in cin["tracker_id"]]]
+        got = handoff.to_tracker_arrays(rows, torch.tensor([n]), tracker_ids=tid)[0]
+        if case["empty"]:
+            assert got["xyxy"].shape == (0, 4)
+            continue
+        assert got["xyxy"].tolist() == case["xyxy"] and str(got["xyxy"].dtype) == case["xyxy_dtype"]
+        assert got["class_id"].tolist() == case["class_id"] and str(got["class_id"].dtype) == case["class_id_dtype"]
+        assert got["confidence"].tolist() == case["confidence"] and str(got["confidence"].dtype) == case["confidence_dtype"]
+        assert (None if got["tracker_id"] is None else got["tracker_id"].tolist()) == case["tracker_id"]
