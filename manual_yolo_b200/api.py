@@ -240,8 +240,9 @@ def _require_dev_accessible(t: torch.Tensor, name: str, dtype):
 
 def _head_levels(head, strides, in_hw, level_hw, allow_pinned=False):
     """C-ABI level descriptors for a concatenated (B,64+nc,A) head or a list of per-level tensors.
-    Returns (levels, n_levels, B, nc, A, device, keepalive)."""
-    _require_cuda = _require_dev_accessible if allow_pinned else globals()["_require_cuda"]
+    Returns (levels, n_levels, B, nc, A, device, keepalive).  ``allow_pinned``: pinned host tensors are accepted
+    (zero-copy reads by the kernel) besides CUDA tensors."""
+    check = _require_dev_accessible if allow_pinned else _require_cuda
     levels = (_lib.Level * 3)()
     if isinstance(head, (list, tuple)):
         if len(head) > 3 or len(head) != len(strides):
@@ -249,7 +250,7 @@ def _head_levels(head, strides, in_hw, level_hw, allow_pinned=False):
         B, no = head[0].shape[:2]
         keep = []
         for l, (x, s) in enumerate(zip(head, strides)):
-            _require_cuda(x, "head level", torch.float32)
+            check(x, "head level", torch.float32)
             if x.dim() != 4 or x.shape[0] != B or x.shape[1] != no:
                 raise ValueError("levels must be (B, 64+nc, Hi, Wi) with equal B and channels")
             if not x.is_cuda and not x.is_contiguous():
@@ -259,7 +260,7 @@ def _head_levels(head, strides, in_hw, level_hw, allow_pinned=False):
             levels[l] = _lib.Level(x.data_ptr(), x.stride(0), x.stride(1), x.shape[2], x.shape[3], float(s))
         n_levels, A, device = len(head), sum(x.shape[2] * x.shape[3] for x in head), head[0].device
     else:
-        _require_cuda(head, "head", torch.float32)
+        check(head, "head", torch.float32)
         if head.dim() != 3:
             raise ValueError("head must be (B, 64+nc, A)")
         if not head.is_cuda and not head.is_contiguous():

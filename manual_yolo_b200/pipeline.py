@@ -333,9 +333,9 @@ class HostRunner:
         return n
 
     def zero_copy_bytes(self, det_rows, det_count):
-        """Bytes the kernels of one step pull from pinned host memory given that step's results: the crop
-        rectangles of the ROI detections (``stage='rows'``) + 256 B per detection candidate is NOT known here, so
-        the DFL part is reported by the caller from the candidate counts."""
+        """Bytes the ROI kernel pulls from the pinned host frames for one step, from that step's results: the crop
+        rectangles of the ROI-class detections (``stage='rows'`` only).  The DFL part of ``dfl_zero_copy`` (64 values
+        per candidate, one 32-byte sector each) is added by the caller from the candidate counts."""
         if self.stage != "rows":
             return 0
         p, H, W = self.pipe, self.pipe.src_hw[0], self.pipe.src_hw[1]
