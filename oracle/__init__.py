@@ -28,6 +28,13 @@ Pinning status
   asserting tests for it (``test_yolo.py`` asserts nothing; ``poker_result.json``
   is empty).  The leaf restatements (numpy fixed-point resize, numpy greedy NMS)
   are checked bit-for-bit against the real cv2 / torchvision leaves instead.
+* Crop geometry (row a12) and the host-side consumers of the result (row a11, N1, N2):
+  **pinned** by golden vectors produced by EXECUTING the reference's own functions, cut out
+  of ``detect.py`` / ``pipe.py`` unmodified (``tests/golden/make_rank_text_golden.py``,
+  ``make_pipe_records_golden.py``, ``make_clean_detections_golden.py``).
+* ``slicing`` (SAHI-style sliced prediction, N3) and ``assoc`` (ByteTrack association
+  costs, N2): restatements of third-party libraries that are not installed here
+  (sahi, supervision==0.26.1): **parity unpinned**, stated in their headers.
 """
 
-from . import assoc, boxes, head, letterbox, nms, roi  # noqa: F401
+from . import assoc, boxes, head, letterbox, nms, roi, slicing  # noqa: F401
