@@ -1,0 +1,81 @@
+"""Randomised sweeps against the oracle (real cv2 / PIL / torchvision leaves): shapes, alignments and sizes no fixed
+case list would enumerate -- odd widths (no 16-byte alignment: the guarded / cooperative-load paths), up- and
+down-scales, crops on every border, window / select boundaries of the sort and NMS kernels.  Bit-exact bar."""
+import numpy as np
+import pytest
+import torch
+
+import manual_yolo_b200 as m
+from manual_yolo_b200 import synth
+from oracle import boxes as oboxes
+from oracle import letterbox as olb
+from oracle import nms as onms
+from oracle import roi as oroi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_letterbox_random_shapes(cuda_dev):
+    rng = np.random.default_rng(7)
+    for it in range(40):
+        H, W = int(rng.integers(20, 1300)), int(rng.integers(20, 2100))
+        imgsz = int(rng.choice([160, 320, 640, 1280]))
+        auto = bool(rng.integers(0, 2))
+        frames = rng.integers(0, 256, (int(rng.integers(1, 3)), H, W, 3), dtype=np.uint8)
+        got = m.preprocess(torch.from_numpy(frames).to(cuda_dev), (imgsz, imgsz), auto=auto).cpu()
+        assert torch.equal(got, olb.preprocess_ref(list(frames), (imgsz, imgsz), auto=auto)), (H, W, imgsz, auto)
+        got8 = m.letterbox(torch.from_numpy(frames[0]).to(cuda_dev), (imgsz, imgsz), auto=auto).cpu().numpy()
+        assert np.array_equal(got8, olb.letterbox_ref(frames[0], (imgsz, imgsz), auto=auto)), (H, W, imgsz, auto)
+
+
+def test_roi_random_boxes_odd_frames(cuda_dev):
+    g = torch.Generator().manual_seed(123)
+    deferred = 0
+    for (H, W) in [(701, 1001), (333, 517), (97, 2049)]:
+        B, N = 2, 400
+        frames = synth.synth_frames(B, H, W, seed=H)
+        w = 4 + torch.rand(N, generator=g) * min(260, W - 2)
+        h = 4 + torch.rand(N, generator=g) * min(260, H - 2)
+        x1 = torch.rand(N, generator=g) * (W + 20) - 10 - w / 2
+        y1 = torch.rand(N, generator=g) * (H + 20) - 10 - h / 2
+        boxes = torch.stack((x1, y1, x1 + w, y1 + h), 1).float()
+        bidx = torch.randint(0, B, (N,), generator=g, dtype=torch.int32)
+        for pad in (0, 6):
+            out, valid = m.crop_resize_rois(frames.to(cuda_dev), boxes.to(cuda_dev), bidx.to(cuda_dev), pad=pad)
+            out, valid = out.cpu(), valid.cpu().tolist()
+            for i in range(N):
+                crop = oboxes.safe_crop_ref(frames[bidx[i]].numpy(), *[int(t) for t in boxes[i]], pad=pad)
+                if crop is None:
+                    assert valid[i] == 0 and float(out[i].abs().max()) == 0.0
+                else:
+                    assert valid[i] in (1, 2) and torch.equal(out[i], oroi.classify_preprocess_ref(crop)), (H, W, pad, i)
+                    deferred += valid[i] == 2
+    assert deferred > 20                                        # both launches were exercised
+
+
+def test_nms_random_sizes_and_overlaps(cuda_dev):
+    g = torch.Generator().manual_seed(99)
+    for it in range(40):
+        A = int(torch.randint(1, 9000, (1,), generator=g))
+        if it % 4 == 0:
+            A = [511, 512, 513, 1024, 1025, 2047, 2048, 2049, 4097, 8400][(it // 4) % 10]      # window / select edges
+        nc, ncl = [1, 3, 80][it % 3], int(torch.randint(1, 400, (1,), generator=g))
+        iou, max_det, agn = float(torch.rand(1, generator=g) * 0.8 + 0.1), [1, 50, 300, 1000][it % 4], it % 5 == 0
+        pred = torch.zeros((2, 4 + nc, A))
+        for b in range(2):
+            centres = torch.rand((ncl, 2), generator=g) * 600 + 20
+            which = torch.randint(0, ncl, (A,), generator=g)
+            jit = float(torch.rand(1, generator=g) * 12)
+            pred[b, 0] = centres[which, 0] + torch.randn(A, generator=g) * jit
+            pred[b, 1] = centres[which, 1] + torch.randn(A, generator=g) * jit
+            pred[b, 2] = 20 + torch.rand(A, generator=g) * 60
+            pred[b, 3] = 20 + torch.rand(A, generator=g) * 60
+            live = torch.randperm(A, generator=g)[: max(1, int(A * float(torch.rand(1, generator=g))))]
+            sc = torch.rand(len(live), generator=g) * 0.9 + 0.05
+            if len(live) > 10:
+                sc[::9] = sc[0]                                                                   # score ties
+            pred[b, 4 + torch.randint(0, nc, (len(live),), generator=g), live] = sc
+        ref_out, ref_idx = onms.non_max_suppression_ref(pred, 0.05, iou, agnostic=agn, max_det=max_det, return_idxs=True)
+        out, idx = m.non_max_suppression(pred.to(cuda_dev), 0.05, iou, agnostic=agn, max_det=max_det, return_idxs=True)
+        for b in range(2):
+            assert torch.equal(idx[b].cpu(), ref_idx[b]) and torch.equal(out[b].cpu(), ref_out[b]), (A, nc, ncl, iou, max_det, agn)
