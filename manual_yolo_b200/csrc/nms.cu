@@ -130,12 +130,9 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
         unsigned long long alive = valid & ~(((unsigned long long)rem_bits[1] << 32) | rem_bits[0]);
         unsigned long long kept = 0;
         int kc = kcount_s;
-        while (alive && kc < max_det) {
+        while (alive && kc < max_det) {                     // the only serial part: bit operations on the mask rows
           const int i = __ffsll((long long)alive) - 1;
           kept |= 1ull << i;
-          keep[kc] = w0 + s + i;
-          kbox[kc] = box[s + i];
-          kmeta[kc] = meta[s + i];
           ++kc;
           alive &= ~mask[i];
           alive &= ~(1ull << i);
@@ -144,6 +141,15 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
         kcount_s = kc;
       }
       __syncthreads();
+      {   // record the chunk's keeps in parallel: rank inside the chunk = number of kept boxes before it
+        const unsigned long long kept = kept_bits_s;
+        if (tid < kChunk && ((kept >> tid) & 1ull)) {
+          const int r = kcount_s - __popcll(kept) + __popcll(kept & ((1ull << tid) - 1ull));
+          keep[r] = w0 + s + tid;
+          kbox[r] = box[s + tid];
+          kmeta[r] = meta[s + tid];
+        }
+      }
       if (kcount_s >= max_det) { done = true; break; }
       // ---- (C) apply this chunk's kept boxes to all later boxes of the window ----
       // Class-aware shortcut (exact, see box_meta): a later box only needs the kept boxes of its own class.
