@@ -226,3 +226,18 @@ def test_batch_stream_two_in_flight(cuda_dev):
     torch.cuda.synchronize()
     for s in range(2):
         _assert_matches(results[4 + s], data[s][2], B)
+
+
+def test_plain_c_host_runs_the_path(cuda_dev, tmp_path):
+    """The C ABI is a boundary for non-Python hosts too: examples/c_host/main.c (gcc, cudaMalloc, no torch) runs
+    letterbox -> class filter -> fused post-processing -> ROI crops and must find its three planted objects."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_host")
+    lib_dir = os.path.join(root, "manual_yolo_b200")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                    os.path.join(root, "examples", "c_host", "main.c"), "-L", lib_dir, "-lb200yolo", "-L", "/usr/local/cuda/lib64",
+                    "-lcudart", "-lm", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    assert "3 detections, 3 ROIs" in r.stdout
