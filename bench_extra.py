@@ -164,6 +164,21 @@ def config1(dev):
     return out
 
 
+def k1_half(dev, B=64):
+    """K1 with fp16 output (predict(half=True) form): half the bytes written."""
+    frames = synth.synth_frames(B, 1200, 1920, seed=0).to(dev)
+    out16 = torch.empty((B, 3, 640, 640), dtype=torch.float16, device=dev)
+    out32 = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, o, half, nbytes in (("f32", out32, False, 4), ("f16", out16, True, 2)):
+        r = timed(lambda: m.preprocess(frames, (640, 640), out=o, half=half), flush=flush)
+        algo = B * (400 * 1920 * 3 + 3 * 640 * 640 * nbytes)
+        r.update(algorithmic_bytes=algo, algo_GBps=algo / (r["us_median"] * 1e-6) / 1e9)
+        res[name] = r
+    return res
+
+
 def calibration(dev):
     """What plain torch copy / fill kernels reach on this GPU for K1's traffic mix (147 MB read, 315 MB written)."""
     out = {}
@@ -218,6 +233,7 @@ def main():
              "config4": ("config4_roi_4096", lambda: config4(dev)),
              "config1": ("config1_single_frame", lambda: config1(dev)),
              "n3": ("n3_sliced_prediction", lambda: config_n3(dev)),
+             "k1half": ("k1_letterbox_f32_vs_f16", lambda: k1_half(dev)),
              "cpu": ("cpu_oracle_threads", lambda: cpu_threads(dev))}
     only = [x for x in args.only.split(",") if x] or list(parts)
     res = {parts[k][0]: parts[k][1]() for k in only}

@@ -65,6 +65,12 @@ const char* b200yolo_strerror(int code);
 int b200yolo_letterbox_u8_to_f32(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
                                  int64_t src_batch_stride, float* dst, int outH, int outW, int new_w,
                                  int new_h, int top, int left, int pad_value, int swap_rb, void* stream);
+/* half=True form (ultralytics predict(half=True): `im.half(); im /= 255` on the device): dst = (B,3,outH,outW)
+ * float16; each value is fl16(fl32(v / 255)), as torch's fp16 division (computed in fp32) rounds it.  Halves the
+ * bytes K1 writes.  The reference runs with half=False (runs/rank_classifier/args.yaml:42): optional. */
+int b200yolo_letterbox_u8_to_f16(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
+                                 int64_t src_batch_stride, void* dst, int outH, int outW, int new_w, int new_h,
+                                 int top, int left, int pad_value, int swap_rb, void* stream);
 int b200yolo_letterbox_u8(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
                           int64_t src_batch_stride, uint8_t* dst, int outH, int outW, int new_w,
                           int new_h, int top, int left, int pad_value, void* stream);

@@ -26,6 +26,8 @@ SIGNATURES = {
     "b200yolo_strerror": (c_char_p, [c_int]),
     "b200yolo_letterbox_u8_to_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_int,
                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200yolo_letterbox_u8_to_f16": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_int,
+                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200yolo_letterbox_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200yolo_decode_filter": (c_int, [POINTER(Level), c_int, c_int, c_int, c_float, c_void_p, c_void_p,

@@ -109,8 +109,9 @@ def stage_rows_h2d(frames_host: torch.Tensor, out: Optional[torch.Tensor] = None
 
 
 def preprocess(frames, new_shape=(640, 640), auto=False, scale_fill=False, scaleup=True, center=True,
-               stride=32, padding_value=114, out=None, src_hw=None):
-    """``BasePredictor.preprocess`` drop-in, fused: uint8 BGR frames -> (B,3,H,W) fp32 RGB in [0,1].
+               stride=32, padding_value=114, out=None, src_hw=None, half=False):
+    """``BasePredictor.preprocess`` drop-in, fused: uint8 BGR frames -> (B,3,H,W) fp32 RGB in [0,1]
+    (``half=True``: float16, the ``predict(half=True)`` form -- ``im.half(); im /= 255``).
 
     ``src_hw``: when given, ``frames`` holds only the rows ``geometry.referenced_rows(src_hw[0], new_h)``
     names (staged by ``stage_rows_h2d``); the letterbox geometry is that of the full (H,W) source and the
@@ -128,14 +129,15 @@ def preprocess(frames, new_shape=(640, 640), auto=False, scale_fill=False, scale
             raise ValueError("staged rows must be the full frame or exactly new_h rows")
     else:
         g = geometry.letterbox_geometry((H, W), new_shape, auto, scale_fill, scaleup, center, stride)
+    dt = torch.float16 if half else torch.float32
     if out is None:
-        out = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=torch.float32, device=frames.device)
-    elif tuple(out.shape) != (B, 3, g["out_h"], g["out_w"]) or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError("out must be a contiguous (B,3,out_h,out_w) float32 tensor")
+        out = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=dt, device=frames.device)
+    elif tuple(out.shape) != (B, 3, g["out_h"], g["out_w"]) or out.dtype != dt or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous (B,3,out_h,out_w) {dt} tensor")
     lib = _lib.load()
-    rc = lib.b200yolo_letterbox_u8_to_f32(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0), _ptr(out),
-                                          g["out_h"], g["out_w"], g["new_w"], g["new_h"], g["top"], g["left"],
-                                          int(padding_value), 1, _stream())
+    fn = lib.b200yolo_letterbox_u8_to_f16 if half else lib.b200yolo_letterbox_u8_to_f32
+    rc = fn(_ptr(frames), B, H, W, frames.stride(1), frames.stride(0), _ptr(out), g["out_h"], g["out_w"], g["new_w"],
+            g["new_h"], g["top"], g["left"], int(padding_value), 1, _stream())
     _lib.check(rc, "preprocess")
     return out
 

@@ -15,6 +15,8 @@
 // (planar RGB) -- or 12 interleaved bytes for the u8 variant.
 // HBM-bound: algorithmic bytes per frame = referenced rows * W*3 + 3*outH*outW*4.
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -75,6 +77,9 @@ template <>
 __device__ __forceinline__ float lb_cast<float>(const float* lut, int v) { return lut[v]; }   // exact v/255 table
 template <>
 __device__ __forceinline__ uint8_t lb_cast<uint8_t>(const float*, int v) { return (uint8_t)v; }
+// half=True (UL `im.half(); im /= 255` on the device): torch divides in fp32 and rounds the quotient to fp16
+template <>
+__device__ __forceinline__ __half lb_cast<__half>(const float* lut, int v) { return __float2half_rn(lut[v]); }
 
 constexpr int kRows = 8;     // output rows per CTA
 constexpr int kStages = 2;   // ring slots: row r+1 is in flight while row r is blended (3 and 4 slots measured: no gain)
@@ -103,6 +108,39 @@ struct OutCursor<float> {
       b200::stg_stream_f4(q0, make_float4(v[0][0], v[1][0], v[2][0], v[3][0]));
       b200::stg_stream_f4(q1, make_float4(v[0][1], v[1][1], v[2][1], v[3][1]));
       b200::stg_stream_f4(q2, make_float4(v[0][2], v[1][2], v[2][2], v[3][2]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n) { q0[k] = v[k][0]; q1[k] = v[k][1]; q2[k] = v[k][2]; }
+    }
+    q0 += row_stride; q1 += row_stride; q2 += row_stride;
+  }
+};
+template <>
+struct OutCursor<__half> {
+  __half *q0, *q1, *q2;    // planes of source channels 0,1,2 (B,G,R): swapped to R,G,B order when swap_rb
+  int64_t row_stride;
+  bool vec;
+  __device__ __forceinline__ void init(const LbParams& p, int b, int oy, int ox, int n) {
+    __half* base = reinterpret_cast<__half*>(p.dst) + ((int64_t)b * 3 * p.outH + oy) * p.outW + ox;
+    const int64_t plane = (int64_t)p.outH * p.outW;
+    q0 = base + (p.swap_rb ? 2 : 0) * plane;
+    q1 = base + plane;
+    q2 = base + (p.swap_rb ? 0 : 2) * plane;
+    row_stride = p.outW;
+    vec = (n == 4) && ((reinterpret_cast<uintptr_t>(base) & 7) == 0) && ((plane & 3) == 0) && ((p.outW & 3) == 0);
+  }
+  __device__ __forceinline__ void store(const __half (&v)[4][3], int n) {
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        __half* q = c == 0 ? q0 : (c == 1 ? q1 : q2);
+        const __half2 lo = __halves2half2(v[0][c], v[1][c]), hi = __halves2half2(v[2][c], v[3][c]);
+        uint2 w;
+        w.x = *reinterpret_cast<const uint32_t*>(&lo);
+        w.y = *reinterpret_cast<const uint32_t*>(&hi);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(q), "r"(w.x), "r"(w.y) : "memory");
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -338,6 +376,13 @@ extern "C" int b200yolo_letterbox_u8_to_f32(const uint8_t* src, int B, int H, in
                                             int swap_rb, void* stream) {
   return launch_letterbox<float>(src, B, H, W, src_pitch, src_batch_stride, dst, outH, outW, new_w, new_h, top,
                                  left, pad_value, swap_rb, stream);
+}
+
+extern "C" int b200yolo_letterbox_u8_to_f16(const uint8_t* src, int B, int H, int W, int64_t src_pitch,
+                                            int64_t src_batch_stride, void* dst, int outH, int outW, int new_w,
+                                            int new_h, int top, int left, int pad_value, int swap_rb, void* stream) {
+  return launch_letterbox<__half>(src, B, H, W, src_pitch, src_batch_stride, dst, outH, outW, new_w, new_h, top, left,
+                                  pad_value, swap_rb, stream);
 }
 
 extern "C" int b200yolo_letterbox_slices_u8_to_f32(const uint8_t* frames, int n_frames, int frame_h, int frame_w,

@@ -96,3 +96,20 @@ def test_letterbox_flags_scaleup_center_scalefill(cuda_dev):
         f = _frames(hw, 5)[0]
         got = m.letterbox(torch.from_numpy(f).to(cuda_dev), (640, 640), **kw).cpu().numpy()
         assert np.array_equal(got, ul(f, (640, 640), **kw)), (hw, kw)
+
+
+def test_half_output_matches_torch_half_semantics(cuda_dev):
+    """half=True form (predict(half=True): `im.half(); im /= 255` on the device): fp16 output equal to torch's own
+    fp16 division of the fp16 image by 255 (computed in fp32, rounded once to fp16) on the oracle's uint8 letterbox,
+    for a down-scale, an odd shape and a slice-sized identity."""
+    from oracle import letterbox as olb
+    rng = np.random.default_rng(5)
+    for (H, W), imgsz in [((1200, 1920), 640), ((543, 770), 1280), ((640, 640), 640), ((333, 517), 320)]:
+        frames = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        got = m.preprocess(torch.from_numpy(frames).to(cuda_dev), (imgsz, imgsz), half=True)
+        assert got.dtype == torch.float16
+        lb = np.stack([olb.letterbox_ref(f, (imgsz, imgsz)) for f in frames])                  # (B,h,w,3) uint8 BGR
+        im = torch.from_numpy(np.ascontiguousarray(lb[..., ::-1].transpose(0, 3, 1, 2))).to(cuda_dev).half()
+        im /= 255                                                                               # torch's fp16 division on the device
+        assert torch.equal(got, im), (H, W, imgsz)
+        assert torch.equal(got.cpu(), olb.preprocess_ref(list(frames), (imgsz, imgsz)).half())
