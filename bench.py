@@ -47,7 +47,7 @@ def _config(n_gpus, extra=None):
     c = {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "frame_hw": list(SRC_HW),
          "anchors": 8400, "nc": NC, "conf": CONF, "iou": IOU, "max_det": MAX_DET,
          "parallelism": f"frame-sharded x{n_gpus}, no collective",
-         "l2_policy": "inputs larger than L2 (717 MB of frames+head per step vs 126 MB L2)"}
+         "l2_policy": "inputs larger than L2 (717 MB of frames+head per step vs 126 MB L2); every batch in flight reads its own copy"}
     if extra:
         c.update(extra)
     return c
@@ -280,7 +280,8 @@ def run_ours(args, rank, world, local):
         pipes = [pipe] + [m.Pipeline(BATCH, SRC_HW, NC, imgsz=IMGSZ, conf=CONF, iou=IOU, max_det=MAX_DET, device=dev,
                                      cap=args.cap or None, overlap=True) for _ in range(depth - 1)]
         bs = m.BatchStream(pipes)
-        bs.capture([(frames_d, head_d)] * depth)
+        # every slot reads its OWN copy of the inputs (same bits): batches in flight cannot feed each other through L2
+        bs.capture([(frames_d, head_d)] + [(frames_d.clone(), head_d.clone()) for _ in range(depth - 1)])
         for _ in range(max(3, args.warmup) * depth):
             bs.submit()
         bs.join()
