@@ -186,7 +186,8 @@ int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float 
  * frames: (B,H,W,3) uint8 BGR; boxes: (N,4) float32 xyxy source pixels; batch_idx: (N) int32;
  * roi_count: optional device int32 -- when non-NULL only the first min(*roi_count, N) ROIs are done.
  * dst: (N,3,size,size) float32 RGB in [0,1] (size must be 64); valid: (N) int32: 1 = ok, 2 = ok and
- * produced by the split large-ROI launch (crop area > 160x160), 0 = safe_crop returns None, -1 = ROI
+ * produced by the general split launch (resample scale > 3 or > 198 referenced columns: far beyond a rank
+ * card), 0 = safe_crop returns None, -1 = ROI
  * beyond the envelope (short side > 31*size); the dst rows of invalid ROIs are zero-filled. */
 int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t pitch,
                              int64_t batch_stride, const float* boxes, const int* batch_idx,

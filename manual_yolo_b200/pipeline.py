@@ -6,8 +6,9 @@ This is the batched, device-resident form of the reference's per-frame loop
 preprocessing (``detect.py:121``).  The backbone/neck stay torch modules outside this package: the
 Detect-head tensor is an input here (``head``), the letterboxed network input an output (``net_in``).
 
-All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 6 launches of
-this package's kernels plus one counter memset, capturable into one CUDA graph.
+All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 5 launches of this
+package's kernels in the sparse regime (7-10 on the general / dense path) plus one counter memset, capturable
+into one CUDA graph.
 """
 
 from __future__ import annotations
