@@ -11,10 +11,13 @@
 // (SURVEY.md Appendix A.11 / B.4).  All size arithmetic (double division, banker's rounding of the
 // crop offset) is done on the device exactly as Python/C do it on the host.
 //
-// One CTA per ROI (384 threads = 3 channels x 64 columns x 2 row phases): 128 threads build the two coefficient tables (only the 64 output columns/rows
-// that survive the centre crop), the horizontal pass writes a uint8 strip into shared memory, the
-// vertical pass streams coalesced fp32 rows to the planar (3,size,size) output.
-// HBM-bound: algorithmic bytes per ROI = crop_h*crop_w*3 read + 3*size*size*4 written.
+// One CTA per ROI.  Two bodies: the fast path (192 threads, every crop up to resample scale 4: see roi_fast_body) and
+// the general body (384 threads = 3 channels x 64 columns x 2 row phases, any scale <= 31, run by roi_big_kernel for
+// the ROIs the fast path defers).  Both build the two coefficient tables for the 64 output columns/rows that survive
+// the centre crop only, write Pillow's uint8 intermediate strip into shared memory (horizontal pass) and stream
+// coalesced fp32 rows to the planar (3,size,size) output (vertical pass).
+// Algorithmic bytes per ROI = crop_h*crop_w*3 read + 3*size*size*4 written; the arithmetic (one 8 x 22-bit
+// integer product per tap) keeps the kernel issue-bound rather than HBM-bound: see DESIGN.md.
 
 #include "common.cuh"
 
@@ -239,49 +242,96 @@ __device__ void roi_body(const uint8_t* __restrict__ frames, const uint8_t* buf_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fast path (first launch): every ROI with <= kFTaps taps per axis (scale <= 3, i.e. short side <= 192) and
-// <= 198 referenced source columns -- every rank card and everything near it.  One CTA of 192 threads per ROI
-// and ~36 KB of shared memory, so 6 CTAs (36 warps) are resident per SM.  There is no CTA-wide staging phase:
-// each warp streams its own source rows through a private ring of 2-3 row buffers filled by 16-byte cp.async
-// (LDGSTS: no registers; rows r+6, r+12 in flight while row r is resampled), so the only CTA barriers are
-// tables -> horizontal pass -> vertical pass.  Crops taller than the uint8 strip are produced in vertical
-// tiles of output rows.  ROIs outside the envelope are marked valid = 2 and produced by roi_big_kernel (the
-// general body above, split over kBigParts CTAs).
+// Fast path (first launch): every ROI with <= kFTaps taps per axis (resample scale <= 4, i.e. short side <= 256)
+// -- every rank card and everything near it.  One CTA of 192 threads per ROI, ~42 KB of shared memory, 5 CTAs
+// (30 warps) per SM.
+//
+//  * staging: each warp streams its own source rows (w, w+6, ..) through a private ring of 2-4 row slots filled by
+//    the TMA engine -- lane 0 issues one 1-D bulk copy per row (cp.async.bulk global->shared completing on the
+//    slot's mbarrier; SASS UBLKCP), so staging costs a handful of instructions per row instead of per-lane
+//    address arithmetic, and rows r+6 .. r+24 are in flight while row r is resampled.  No CTA barrier inside the
+//    horizontal pass (a CTA-wide chunked stage with one barrier per chunk was measured: 183 us vs 143 us).
+//  * horizontal pass: warp w resamples rows w, w+6, .. of the tile; lane owns output columns lane and lane+32
+//    (3 channels each: conflict-free byte reads), weights in registers, taps unrolled to the crop's exact tap
+//    class (2/3/4/5/6/8/10: up-scales have 2).  The weights are stored pre-shifted by 2 bits, so the rounded
+//    uint8 result is the TOP BYTE of the 32-bit accumulator.
+//  * vertical pass: thread = (channel, 4 adjacent columns) of one output row, one 32-bit LDS feeds 4 accumulators
+//    per tap, taps unrolled to the tap class; v/255 exactly as torch divides, computed in the FMA pipe (no table:
+//    no bank conflicts); one 128-bit streaming store per 4 outputs.
+// Crops taller than the uint8 strip are produced in vertical tiles of output rows.  ROIs outside the envelope are
+// marked valid = 2 and produced by roi_big_kernel (the general body above, split over kBigParts CTAs).
 constexpr int kFT = 192;          // threads: 6 warps
 constexpr int kFWarps = kFT / 32;
-constexpr int kFTaps = 8;         // taps per axis (ksize = 2*ceil(scale)+1 <= 7 for scale <= 3)
-constexpr int kFRows = 116;       // uint8 strip rows: source rows one vertical tile may reference (tallest rank crop: 115)
-constexpr int kPool = 1248;       // per-warp row-buffer pool: 3 rows of <= 416 B or 2 rows of <= 624 B
-constexpr int kRingMax = 3;       // rows in flight per warp
+constexpr int kFTaps = 10;        // taps per axis (ksize = 2*ceil(scale)+1 <= 9 for scale <= 4)
+constexpr int kFKy = 12;          // vertical weight row, padded to int4 multiples
+constexpr int kFRows = 106;       // uint8 strip rows: source rows one vertical tile may reference (tallest rank crop: 105)
+constexpr int kPool = 1248;       // per-warp row-slot pool: 4 rows of <= 304 B, 3 of <= 416 B, 2 of <= 624 B, 1 of <= 1248 B
+constexpr int kRingMax = 4;       // rows in flight per warp
+constexpr uint32_t kRnd4 = 1u << (kPrec + 1);   // Pillow's 2^(PRECISION_BITS-1) rounding term, in the <<2 domain
+constexpr double kSegScale = 1.3; // two-segment launches: crops down-scaled by more than this run first
+constexpr int kSegMinRois = 1024; // ... when the launch holds at least this many ROIs (more than one wave of CTAs)
 
 struct FastSmem {
-  int xk[kFTaps][kS];             // horizontal weights, transposed (conflict-free per warp)
-  int yk[kS][kFTaps];             // vertical weights (broadcast reads)
+  uint32_t xk[kFTaps][kS];        // horizontal weights << 2, transposed (conflict-free per warp)
+  uint32_t yk[kS][kFKy];          // vertical weights << 2 (broadcast reads)
   int xb[kS][2];                  // (xmin, count) per surviving output column
   int yb[kS][2];                  // per surviving output row
   uint8_t strip[kFRows + kFTaps][3][kS];  // horizontal-pass output (Pillow's uint8 intermediate image) + rows that
                                           // only zero-weight taps of the unrolled vertical pass may touch
-  float lut[256];                 // v / 255 exactly as torch's fp32 division rounds it
   __align__(16) uint8_t ring[kFWarps][kPool];
-  __align__(16) uint8_t slack[32];  // zero-weight taps of the last ring row may read (never use) up to 23 bytes past it
+  __align__(16) uint8_t slack[48];  // zero-weight taps of the last staged row may read (never use) bytes past it
+  __align__(8) uint64_t bar[kFWarps][kRingMax];
   int sel[4];
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(b200::smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // Pillow's clip8 clamps (acc >> 22) to [0,255].  For the bilinear (triangle) filter every weight is >= 0 and the
 // fixed-point weights of one output sum to at most 2^22 + taps/2, so 0 <= acc = 2^21 + sum(p_i * k_i)
-// <= 2^21 + 255 * (2^22 + 4) < 256 * 2^22: the clamp can never act and the fast path omits it (the general body
-// keeps it; both are compared bit-for-bit against PIL in tests/test_gpu_roi.py).
-__device__ __forceinline__ int shr22(int acc) { return acc >> kPrec; }
+// <= 2^21 + 255 * (2^22 + 5) < 256 * 2^22: the clamp can never act and the fast path omits it (the general body
+// keeps it; both are compared bit-for-bit against PIL in tests/test_gpu_roi.py).  Hence 4 * acc < 2^32: with the
+// weights and the rounding term pre-shifted by two bits the unsigned accumulator holds acc >> 22 in its top byte.
 
-// pil_axis for the fast path: <= kFTaps weights returned in registers, zero-padded, each tap evaluated once.
-__device__ __forceinline__ int pil_axis8(int o, int in_size, int out_size, int (&k)[kFTaps], int& cnt_out) {
+// (a >> 24) / 255 exactly as torch's fp32 division rounds it, without a table: v = a >> 24 is built as the float
+// 2^23 + v by one byte permute, v/255 = RN(v * c_hi + RN(v * c_lo)) with c_hi + c_lo = 1/255 to 48 bits -- equal to
+// IEEE v / 255.0f for every v in [0, 255] (checked exhaustively on the host in tests/test_host_logic.py and, through
+// every K5 output, against PIL on the device).
+__device__ __forceinline__ float top_byte_div255(uint32_t a) {
+  const float v = __fsub_rn(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7443)), 8388608.0f);
+  return __fmaf_rn(v, __uint_as_float(0x3B808081u), __fmul_rn(v, __uint_as_float(0xAF7F00BFu)));
+}
+// The same for two accumulators at once with Blackwell's packed fp32 pipe (SASS FADD2 / FMUL2 / FFMA2).
+__device__ __forceinline__ float2 top_byte_div255_x2(uint32_t a, uint32_t b) {
+  float2 d;
+  asm("{\n\t"
+      ".reg .b64 x, v, t, m, cl, ch;\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 m, {%4, %4};\n\t"
+      "mov.b64 cl, {%5, %5};\n\t"
+      "mov.b64 ch, {%6, %6};\n\t"
+      "add.rn.f32x2 v, x, m;\n\t"
+      "mul.rn.f32x2 t, v, cl;\n\t"
+      "fma.rn.f32x2 t, v, ch, t;\n\t"
+      "mov.b64 {%0, %1}, t;\n\t"
+      "}"
+      : "=f"(d.x), "=f"(d.y)
+      : "r"(__byte_perm(a, 0x4B000000u, 0x7443)), "r"(__byte_perm(b, 0x4B000000u, 0x7443)), "f"(-8388608.0f),
+        "f"(__uint_as_float(0xAF7F00BFu)), "f"(__uint_as_float(0x3B808081u)));
+  return d;
+}
+
+// x is the same in every lane: returns it in a form the compiler knows to be warp-uniform (REDUX writes a uniform
+// register), so the address arithmetic that feeds the bulk copies stays in the uniform datapath.
+__device__ __forceinline__ uint32_t uni(uint32_t x) { return __reduce_max_sync(0xffffffffu, x); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for output index `o` (triangle filter), fast-path form: the
+// (<= kFTaps) weights go straight to shared memory, pre-shifted, zero-filled up to `pad` entries.  Same double
+// arithmetic, in the same order, as pil_axis above.
+__device__ __forceinline__ int pil_axis_fast(int o, int in_size, int out_size, uint32_t* coef, int cstride, int pad,
+                                             int& cnt_out) {
   const double scale = __ddiv_rn((double)in_size, (double)out_size);
   const double fscale = scale < 1.0 ? 1.0 : scale;
   const double ss = __ddiv_rn(1.0, fscale);
@@ -291,46 +341,166 @@ __device__ __forceinline__ int pil_axis8(int o, int in_size, int out_size, int (
   int xmax = __double2int_rz(__dadd_rn(__dadd_rn(center, fscale), 0.5));
   if (xmax > in_size) xmax = in_size;
   xmax -= xmin;
-  if (xmax > kFTaps) xmax = kFTaps;  // unreachable inside the fast envelope (scale <= 3 -> <= 7 taps)
-  double w[kFTaps], ww = 0.0;
-#pragma unroll
-  for (int x = 0; x < kFTaps; ++x) {
+  if (xmax > kFTaps) xmax = kFTaps;  // unreachable inside the fast envelope (scale <= 4 -> <= 9 taps)
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
     double v = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
     if (v < 0.0) v = -v;
-    w[x] = (x < xmax && v < 1.0) ? __dsub_rn(1.0, v) : 0.0;
-    if (x < xmax) ww = __dadd_rn(ww, w[x]);            // same left-to-right order as Pillow's loop
+    const double w = v < 1.0 ? __dsub_rn(1.0, v) : 0.0;
+    ww = __dadd_rn(ww, w);
   }
-#pragma unroll
-  for (int x = 0; x < kFTaps; ++x) {
-    k[x] = 0;
-    if (x < xmax) {
-      const double q = ww != 0.0 ? __ddiv_rn(w[x], ww) : w[x];
-      k[x] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(q, (double)(1 << kPrec))));
-    }
+  for (int x = 0; x < xmax; ++x) {
+    double v = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    if (v < 0.0) v = -v;
+    double w = v < 1.0 ? __dsub_rn(1.0, v) : 0.0;
+    if (ww != 0.0) w = __ddiv_rn(w, ww);
+    coef[x * cstride] = (uint32_t)__double2int_rz(__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrec)))) << 2;
   }
+  for (int x = xmax; x < pad; ++x) coef[x * cstride] = 0u;
   cnt_out = xmax;
   return xmin;
 }
 
+// Everything the two passes of one vertical tile share (CTA-uniform).
+struct FastTile {
+  const uint8_t* row0;      // global address of the first referenced byte of the tile's first source row
+  const uint8_t* frames;    // caller's buffer bounds (guarded path)
+  const uint8_t* buf_hi;
+  int64_t pitch;
+  int rows;                 // source rows the tile references
+  int span;                 // referenced bytes per row
+  int row_stride;           // staged row pitch (worst 16-byte phase + span, multiple of 16)
+  int nslots;               // ring slots per warp (2..kRingMax)
+  bool inside;              // every 16-byte chunk of every row lies inside the caller's buffer
+};
+
 // One source row -> 6 strip bytes per lane (columns lane and lane+32, 3 channels), T taps unrolled; taps beyond a
 // column's count have weight 0 (their bytes are whatever follows in the ring: read, never used).
 template <int T>
-__device__ __forceinline__ void hrow(const uint8_t* p, const uint8_t* q, const int (&k0)[kFTaps], const int (&k1)[kFTaps],
-                                     uint8_t* so, int lane) {
+__device__ __forceinline__ void hrow(const uint8_t* __restrict__ p, const uint8_t* __restrict__ q,
+                                     const uint32_t (&k0)[T], const uint32_t (&k1)[T], uint8_t* __restrict__ so) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    int a = 1 << (kPrec - 1), b = 1 << (kPrec - 1);
+    uint32_t a = kRnd4, b = kRnd4;
 #pragma unroll
-    for (int t = 0; t < T; ++t) { a += (int)p[3 * t + c] * k0[t]; b += (int)q[3 * t + c] * k1[t]; }
-    so[c * kS + lane] = (uint8_t)shr22(a);
-    so[c * kS + lane + 32] = (uint8_t)shr22(b);
+    for (int t = 0; t < T; ++t) { a += (uint32_t)p[3 * t + c] * k0[t]; b += (uint32_t)q[3 * t + c] * k1[t]; }
+    so[c * kS] = (uint8_t)(a >> 24);
+    so[c * kS + 32] = (uint8_t)(b >> 24);
+  }
+}
+
+// Horizontal pass of one vertical tile: warp w owns source rows w, w+6, ..  (sidx, parity) is the warp's ring cursor:
+// slots are used round-robin, the cursor keeps running across tiles, and every slot completes one mbarrier phase per
+// round, so one parity bit (flipped when the cursor wraps) serves all slots.
+template <int T>
+__device__ __forceinline__ void hpass(FastSmem& sm, const FastTile& t, int xo0, int xo1, uint32_t& sidx,
+                                      uint32_t& parity, int tid) {
+  const int lane = tid & 31;
+  const uint32_t wid = uni((uint32_t)tid >> 5);
+  uint32_t k0[T], k1[T];
+#pragma unroll
+  for (int i = 0; i < T; ++i) { k0[i] = sm.xk[i][lane]; k1[i] = sm.xk[i][lane + 32]; }
+  // warp-uniform copies of the tile parameters (they come from shared / global loads: the compiler cannot tell)
+  const uint32_t rows = uni((uint32_t)t.rows), span = uni((uint32_t)t.span), rstride = uni((uint32_t)t.row_stride);
+  const uint32_t nslots = uni((uint32_t)t.nslots);
+  const uint64_t row0 = ((uint64_t)uni((uint32_t)(reinterpret_cast<uintptr_t>(t.row0) >> 32)) << 32) |
+                        uni((uint32_t)reinterpret_cast<uintptr_t>(t.row0));
+  uint8_t* const ring = &sm.ring[0][0] + wid * kPool;
+  const uint32_t ring_a = b200::smem_u32(&sm.ring[0][0]) + wid * kPool;
+  const uint32_t bar_a = b200::smem_u32(&sm.bar[0][0]) + wid * (8 * kRingMax);
+  const uint32_t pstep = (uint32_t)(t.pitch & 15), dph = (kFWarps * pstep) & 15u;
+  uint32_t ph = ((uint32_t)(row0 & 15) + wid * pstep) & 15u;   // 16-byte phase of row j
+  uint8_t* so = &sm.strip[0][0][lane] + wid * (3 * kS);
+  const uint64_t step = (uint64_t)kFWarps * (uint64_t)t.pitch;
+  if (uni(t.inside ? 1u : 0u)) {
+    uint64_t gi = row0 + (uint64_t)wid * (uint64_t)t.pitch;    // next row to issue, its index and phase
+    uint32_t ji = wid, phi = ph;
+    auto issue = [&](uint32_t s) {
+      if (ji < rows) {
+        if (elect_one()) {
+          const uint32_t nb = (phi + span + 15u) & ~15u;
+          b200::mbar_expect_tx_addr(bar_a + 8u * s, nb);
+          b200::bulk_g2s_addr(ring_a + s * rstride, reinterpret_cast<const void*>(gi - phi), nb, bar_a + 8u * s);
+        }
+      }
+      gi += step; ji += kFWarps; phi = (phi + dph) & 15u;
+    };
+    {
+      uint32_t s = sidx;
+      for (uint32_t r = 0; r < nslots; ++r) { issue(s); s = s + 1u == nslots ? 0u : s + 1u; }
+    }
+    for (uint32_t j = wid; j < rows; j += kFWarps) {
+      b200::mbar_wait_addr(bar_a + 8u * sidx, parity);
+      const uint8_t* rb = ring + sidx * rstride + ph;
+      hrow<T>(rb + xo0, rb + xo1, k0, k1, so);
+      __syncwarp();                                          // every lane is done with this slot before it is refilled
+      issue(sidx);
+      so += kFWarps * 3 * kS;
+      ph = (ph + dph) & 15u;
+      if (++sidx == nslots) { sidx = 0; parity ^= 1u; }
+    }
+  } else {
+    // crop touching the first/last bytes of the caller's allocation: guarded word loads into slot 0, no bulk copy
+    // (which could start before / end after the buffer), no barrier
+    const uint8_t* g = t.row0 + (int64_t)wid * t.pitch;
+    for (uint32_t j = wid; j < rows; j += kFWarps, g += step, so += kFWarps * 3 * kS, ph = (ph + dph) & 15u) {
+      const int nchunk16 = (int)((ph + span + 15u) >> 4);
+      for (int ck = lane; ck < nchunk16; ck += 32) {
+        uint32_t* dw = reinterpret_cast<uint32_t*>(ring + ck * 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dw[u] = load_word_guarded(g - ph + ck * 16 + 4 * u, t.frames, t.buf_hi);
+      }
+      __syncwarp();
+      hrow<T>(ring + ph + xo0, ring + ph + xo1, k0, k1, so);
+      __syncwarp();
+    }
+  }
+}
+
+// Vertical pass + BGR->RGB + /255 for output rows [t0, t1).  Per round of 4 rows: warps {0,1} / {3,4} take channels
+// 0-1 of two rows (lane -> channel = lane/16, column quad = lane%16), warps 2 / 5 take channel 2 of both -- every
+// LDS.32 of a warp is bank-conflict free (rows of one warp are identical or 48 words apart).
+template <int T>
+__device__ __forceinline__ void vpass(FastSmem& sm, int t0, int t1, int rmin, float* __restrict__ out, int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+  const int w3 = wid % 3, half = lane >> 4;
+  const int vc = w3 == 2 ? 2 : half;
+  const int rsel = 2 * (wid / 3) + (w3 == 2 ? half : w3);
+  const int vx = (lane & 15) * 4;
+  float* o = out + ((2 - vc) * kS + t0 + rsel) * kS + vx;
+  const uint8_t* spb = &sm.strip[0][vc][vx] - rmin * (3 * kS);
+  const int* ybp = &sm.yb[t0 + rsel][0];
+  const uint32_t* kq = &sm.yk[t0 + rsel][0];
+  for (int yy = t0 + rsel; yy < t1; yy += 4, o += 4 * kS, ybp += 4 * 2, kq += 4 * kFKy) {
+    const uint8_t* sp = spb + *ybp * (3 * kS);
+    uint32_t kv[((T + 3) / 4) * 4];
+#pragma unroll
+    for (int i = 0; i < (T + 3) / 4; ++i) {
+      const uint4 v = *reinterpret_cast<const uint4*>(kq + 4 * i);
+      kv[4 * i] = v.x; kv[4 * i + 1] = v.y; kv[4 * i + 2] = v.z; kv[4 * i + 3] = v.w;
+    }
+    uint32_t a0 = kRnd4, a1 = kRnd4, a2 = kRnd4, a3 = kRnd4;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(sp + t * (3 * kS));
+      a0 += (w & 0xffu) * kv[t];
+      a1 += __byte_perm(w, 0u, 0x4441) * kv[t];
+      a2 += __byte_perm(w, 0u, 0x4442) * kv[t];
+      a3 += (w >> 24) * kv[t];
+    }
+    const float2 lo = top_byte_div255_x2(a0, a1), hi = top_byte_div255_x2(a2, a3);
+    b200::stg_stream_f4(o, make_float4(lo.x, lo.y, hi.x, hi.y));
   }
 }
 
 __device__ void roi_fast_body(const uint8_t* __restrict__ frames, const uint8_t* buf_hi, int B, int H, int W,
                               int64_t pitch, int64_t bstride, int bi, int bx1, int by1, int bx2, int by2, int pad,
-                              float* __restrict__ out, int* __restrict__ valid_out, FastSmem& sm) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+                              float* __restrict__ out, int* __restrict__ valid_out, FastSmem& sm, int seg) {
+  // seg: -1 = produce this ROI; 0 / 1 = the launch runs every ROI through two grid segments and this CTA belongs to
+  // the first / second: the first produces only the long-running crops (down-scales beyond kSegScale), the second
+  // the rest -- the hardware dispatches CTAs in index order, so the long ones start first and the short ones fill
+  // in behind them (longest-processing-time-first: the tail of the launch is a short crop, not a long one).
+  const int tid = threadIdx.x, lane = tid & 31;
   // ---- safe_crop (detect.py:100-113) ----
   const int cx1 = max(0, min(W - 1, bx1 - pad)), cx2 = max(0, min(W, bx2 + pad));
   const int cy1 = max(0, min(H - 1, by1 - pad)), cy2 = max(0, min(H, by2 + pad));
@@ -342,9 +512,13 @@ __device__ void roi_fast_body(const uint8_t* __restrict__ frames, const uint8_t*
     if (cw <= ch) new_h = __double2int_rz(__ddiv_rn((double)(kS * (int64_t)ch), (double)cw));
     else new_w = __double2int_rz(__ddiv_rn((double)(kS * (int64_t)cw), (double)ch));
     const double sx = (double)cw / (double)new_w, sy = (double)ch / (double)new_h;
-    const int cs = (int)ceil(fmax(fmax(sx, sy), 1.0));
+    const double smax = fmax(fmax(sx, sy), 1.0);
+    const int cs = (int)ceil(smax);
+    if (seg >= 0 && (seg == 0) != (smax > kSegScale)) return;          // the other segment's CTA produces this ROI
     if (2 * cs + 1 > kMaxTaps) { ok = false; unsupported = true; }     // beyond the general body's envelope too
-    else if (2 * cs + 1 > kFTaps) defer = true;                        // scale > 3: general body
+    else if (2 * cs + 1 > kFTaps) defer = true;                        // scale > 4: general body
+  } else if (seg == 0) {
+    return;                                                            // invalid ROIs are zero-filled by segment 1
   }
   if (!ok) {
     for (int i = tid; i < 3 * kS * kS / 4; i += kFT) reinterpret_cast<float4*>(out)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -354,43 +528,36 @@ __device__ void roi_fast_body(const uint8_t* __restrict__ frames, const uint8_t*
   if (defer) { if (tid == 0) *valid_out = 2; return; }
   const int left = half_round_even(new_w - kS), top = half_round_even(new_h - kS);
 
-  // ---- coefficient tables: threads 0..63 horizontal (own column), 64..127 vertical (own row); 128.. the LUT ----
+  // ---- coefficient tables: threads 0..63 horizontal (own column), 64..127 vertical (own row); 128 the barriers ----
   if (tid < kS) {
-    int cnt, k[kFTaps];
-    const int xm = pil_axis8(left + tid, cw, new_w, k, cnt);
-#pragma unroll
-    for (int t = 0; t < kFTaps; ++t) sm.xk[t][tid] = k[t];
+    int cnt;
+    const int xm = pil_axis_fast(left + tid, cw, new_w, &sm.xk[0][tid], kS, kFTaps, cnt);
     sm.xb[tid][0] = xm; sm.xb[tid][1] = cnt;
   } else if (tid < 2 * kS) {
     const int yy = tid - kS;
-    int cnt, k[kFTaps];
-    const int ymin = pil_axis8(top + yy, ch, new_h, k, cnt);
-    *reinterpret_cast<int4*>(&sm.yk[yy][0]) = make_int4(k[0], k[1], k[2], k[3]);
-    *reinterpret_cast<int4*>(&sm.yk[yy][4]) = make_int4(k[4], k[5], k[6], k[7]);
+    int cnt;
+    const int ymin = pil_axis_fast(top + yy, ch, new_h, &sm.yk[yy][0], 1, kFKy, cnt);
     sm.yb[yy][0] = ymin; sm.yb[yy][1] = cnt;
-  } else {
-    for (int v = tid - 2 * kS; v < 256; v += kFT - 2 * kS) sm.lut[v] = b200::u8_div255(v);
+  } else if (tid - 2 * kS < kFWarps * kRingMax) {
+    b200::mbar_init(&sm.bar[0][0] + (tid - 2 * kS), 1);
+    b200::mbar_fence_init();
   }
   __syncthreads();
-  const int x_lo = sm.xb[0][0], span = (sm.xb[kS - 1][0] + sm.xb[kS - 1][1] - x_lo) * 3;   // bounds are monotone
-  const int row_stride = (15 + span + 15) & ~15;            // worst 16-byte phase + referenced bytes, in chunks
-  const int nslots = min(kRingMax, kPool / row_stride);
-  if (nslots < 2) {                                         // uniform: row wider than the fast envelope
+  FastTile t;
+  t.frames = frames; t.buf_hi = buf_hi; t.pitch = pitch;
+  const int x_lo = sm.xb[0][0];
+  t.span = (sm.xb[kS - 1][0] + sm.xb[kS - 1][1] - x_lo) * 3;   // bounds are monotone
+  t.row_stride = (15 + t.span + 15) & ~15;                     // worst 16-byte phase + referenced bytes, in chunks
+  t.nslots = 4 * t.row_stride <= kPool ? 4 : (3 * t.row_stride <= kPool ? 3 : (2 * t.row_stride <= kPool ? 2 : (t.row_stride <= kPool ? 1 : 0)));
+  if (t.nslots < 1) {                                          // uniform: row wider than the fast envelope (cannot happen for <= kFTaps taps)
     if (tid == 0) *valid_out = 2;
     return;
   }
   // per-thread horizontal set-up: lane owns output columns lane and lane+32 of every row its warp resamples
   const int xo0 = (sm.xb[lane][0] - x_lo) * 3, xo1 = (sm.xb[lane + 32][0] - x_lo) * 3;
-  const int c0 = sm.xb[lane][1], c1 = sm.xb[lane + 32][1];
-  const int cmax = __reduce_max_sync(0xffffffffu, max(c0, c1));   // warp-uniform tap class: 3, 4, 6 or 8 unrolled taps
-  const int ycmax = __reduce_max_sync(0xffffffffu, max(sm.yb[lane][1], sm.yb[lane + 32][1]));
-  int k0[kFTaps], k1[kFTaps];
-#pragma unroll
-  for (int t = 0; t < kFTaps; ++t) { k0[t] = sm.xk[t][lane]; k1[t] = sm.xk[t][lane + 32]; }   // zero beyond the count
-  uint8_t* myring = &sm.ring[wid][0];
-  const int vq = tid % 48, vph = tid / 48;                  // vertical pass: (channel, column quad), 4 row phases
-  const int vc = vq >> 4, vx = (vq & 15) * 4;
-  float* orow = out + (2 - vc) * kS * kS + vx;
+  const int cmax = __reduce_max_sync(0xffffffffu, max(sm.xb[lane][1], sm.xb[lane + 32][1]));     // CTA-uniform
+  const int ycmax = __reduce_max_sync(0xffffffffu, max(sm.yb[lane][1], sm.yb[lane + 32][1]));    // tap classes
+  uint32_t sidx = 0, parity = 0;                               // this warp's ring cursor
 
   int t0 = 0;
   while (t0 < kS) {
@@ -401,79 +568,26 @@ __device__ void roi_fast_body(const uint8_t* __restrict__ frames, const uint8_t*
       t1 = t0 + 1;
       while (t1 < kS && sm.yb[t1][0] + sm.yb[t1][1] - rmin <= kFRows) ++t1;
     }
-    const int rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
-    // ---- horizontal pass: warp w owns source rows w, w+6, .. of the tile ----
-    {
-      const uint8_t* row0 = frames + (int64_t)bi * bstride + (int64_t)(cy1 + rmin) * pitch + (int64_t)(cx1 + x_lo) * 3;
-      // every 16-byte chunk of every row of the tile inside the caller's buffer?  (false only for crops touching
-      // the first/last bytes of the allocation: those rows take the guarded path)
-      const bool inside = (row0 - 15 >= frames) && (row0 + (int64_t)(rows - 1) * pitch + span + 31 <= buf_hi);
-      const int64_t step = (int64_t)kFWarps * pitch;
-      const uint8_t* gi = row0 + (int64_t)wid * pitch;      // next row to issue
-      int ji = wid;
-      auto issue = [&](int slot) {
-        if (ji < rows) {
-          const int ph = (int)(reinterpret_cast<uintptr_t>(gi) & 15);
-          const int nchunk = (ph + span + 15) >> 4;         // <= row_stride / 16 <= 39
-          const uint8_t* a = gi - ph + lane * 16;
-          uint8_t* d = myring + slot * row_stride + lane * 16;
-          if (inside) {
-            if (lane < nchunk) cp_async16(d, a);
-            if (lane + 32 < nchunk) cp_async16(d + 512, a + 512);
-          } else {
-            for (int ck = lane; ck < nchunk; ck += 32, a += 512, d += 512) {
-              uint32_t* dw = reinterpret_cast<uint32_t*>(d);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dw[q] = load_word_guarded(a + 4 * q, frames, buf_hi);
-            }
-          }
-        }
-        cp_async_commit();
-        gi += step; ji += kFWarps;
-      };
-      for (int r = 0; r < nslots; ++r) issue(r);
-      int slot = 0;
-      const uint8_t* g = row0 + (int64_t)wid * pitch;       // row being resampled
-      uint8_t* so = &sm.strip[wid][0][0];
-      for (int j = wid; j < rows; j += kFWarps, g += step, so += kFWarps * 3 * kS) {
-        if (nslots == 3) cp_async_wait<2>(); else cp_async_wait<1>();
-        __syncwarp();
-        const uint8_t* rb = myring + slot * row_stride + (int)(reinterpret_cast<uintptr_t>(g) & 15);
-        if (cmax <= 3) hrow<3>(rb + xo0, rb + xo1, k0, k1, so, lane);
-        else if (cmax <= 4) hrow<4>(rb + xo0, rb + xo1, k0, k1, so, lane);
-        else if (cmax <= 6) hrow<6>(rb + xo0, rb + xo1, k0, k1, so, lane);
-        else hrow<8>(rb + xo0, rb + xo1, k0, k1, so, lane);
-        __syncwarp();                                      // every lane is done with this slot before it is refilled
-        issue(slot);
-        slot = slot + 1 == nslots ? 0 : slot + 1;
-      }
-      cp_async_wait<0>();
+    t.rows = sm.yb[t1 - 1][0] + sm.yb[t1 - 1][1] - rmin;
+    t.row0 = frames + (int64_t)bi * bstride + (int64_t)(cy1 + rmin) * pitch + (int64_t)(cx1 + x_lo) * 3;
+    t.inside = (t.row0 - 15 >= frames) && (t.row0 + (int64_t)(t.rows - 1) * pitch + t.span + 31 <= buf_hi);
+    switch (cmax) {
+      case 1: case 2: hpass<2>(sm, t, xo0, xo1, sidx, parity, tid); break;
+      case 3: hpass<3>(sm, t, xo0, xo1, sidx, parity, tid); break;
+      case 4: hpass<4>(sm, t, xo0, xo1, sidx, parity, tid); break;
+      case 5: hpass<5>(sm, t, xo0, xo1, sidx, parity, tid); break;
+      case 6: hpass<6>(sm, t, xo0, xo1, sidx, parity, tid); break;
+      case 7: case 8: hpass<8>(sm, t, xo0, xo1, sidx, parity, tid); break;
+      default: hpass<kFTaps>(sm, t, xo0, xo1, sidx, parity, tid); break;
     }
-    __syncthreads();
-    // ---- vertical pass + BGR->RGB + /255: one 32-bit LDS feeds 4 accumulators per tap, one 128-bit store
-    //      per 4 outputs; taps unrolled to the crop's tap class (weights beyond a row's count are 0 and the
-    //      strip has slack rows, so the extra taps read but never contribute) ----
-    for (int yy = t0 + vph; yy < t1; yy += kFT / 48) {
-      const int ymin = sm.yb[yy][0] - rmin;
-      int a0 = 1 << (kPrec - 1), a1 = a0, a2 = a0, a3 = a0;
-      const uint8_t* sp = &sm.strip[ymin][vc][vx];
-      auto tap = [&](const uint8_t* s1, int kv) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(s1);
-        a0 += (int)(w & 0xff) * kv;
-        a1 += (int)((w >> 8) & 0xff) * kv;
-        a2 += (int)((w >> 16) & 0xff) * kv;
-        a3 += (int)(w >> 24) * kv;
-      };
-      const int4 ka = *reinterpret_cast<const int4*>(&sm.yk[yy][0]);
-      tap(sp, ka.x); tap(sp + 3 * kS, ka.y); tap(sp + 2 * 3 * kS, ka.z);
-      if (ycmax > 3) {
-        tap(sp + 3 * 3 * kS, ka.w);
-        if (ycmax > 4) {
-          const int4 kb = *reinterpret_cast<const int4*>(&sm.yk[yy][4]);
-          tap(sp + 4 * 3 * kS, kb.x); tap(sp + 5 * 3 * kS, kb.y); tap(sp + 6 * 3 * kS, kb.z); tap(sp + 7 * 3 * kS, kb.w);
-        }
-      }
-      b200::stg_stream_f4(orow + yy * kS, make_float4(sm.lut[shr22(a0)], sm.lut[shr22(a1)], sm.lut[shr22(a2)], sm.lut[shr22(a3)]));
+    __syncthreads();                                       // the strip is complete
+    switch (ycmax) {
+      case 1: case 2: vpass<2>(sm, t0, t1, rmin, out, tid); break;
+      case 3: vpass<3>(sm, t0, t1, rmin, out, tid); break;
+      case 4: vpass<4>(sm, t0, t1, rmin, out, tid); break;
+      case 5: case 6: vpass<6>(sm, t0, t1, rmin, out, tid); break;
+      case 7: case 8: vpass<8>(sm, t0, t1, rmin, out, tid); break;
+      default: vpass<kFTaps>(sm, t0, t1, rmin, out, tid); break;
     }
     if (t1 < kS) __syncthreads();                          // the strip is rewritten by the next tile
     t0 = t1;
@@ -486,15 +600,17 @@ __global__ void __launch_bounds__(kFT, 6) roi_kernel(const uint8_t* __restrict__
                                                      int H, int W, int64_t pitch, int64_t bstride,
                                                      const float* __restrict__ boxes, const int* __restrict__ batch_idx,
                                                      const int* __restrict__ roi_count, int pad,
-                                                     float* __restrict__ dst, int* __restrict__ valid) {
+                                                     float* __restrict__ dst, int* __restrict__ valid, int N) {
   extern __shared__ __align__(16) uint8_t roi_smem[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(roi_smem);
-  const int r = blockIdx.x;
+  // grid = N (one segment) or 2N (two segments: see roi_fast_body)
+  const int seg = gridDim.x > (unsigned)N ? (int)(blockIdx.x >= (unsigned)N) : -1;
+  const int r = blockIdx.x - (seg > 0 ? N : 0);
   if (roi_count != nullptr && r >= *roi_count) return;
   // int() truncation of the float box (detect.py:581)
   const float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)r * 4);
   roi_fast_body(frames, buf_hi, B, H, W, pitch, bstride, batch_idx[r], __float2int_rz(bx.x), __float2int_rz(bx.y),
-                __float2int_rz(bx.z), __float2int_rz(bx.w), pad, dst + (int64_t)r * 3 * kS * kS, valid + r, sm);
+                __float2int_rz(bx.z), __float2int_rz(bx.w), pad, dst + (int64_t)r * 3 * kS * kS, valid + r, sm, seg);
 }
 
 // Detection form (pipeline): CTA g locates the g-th detection (image-major, rank order) whose class is in
@@ -560,7 +676,7 @@ __global__ void __launch_bounds__(kFT, 6) roi_det_kernel(const uint8_t* __restri
   const float* row = det + ((int64_t)b * max_det + i) * 6;
   if (tid == 0) { roi_batch[g] = b; roi_det[g] = i; }
   roi_fast_body(frames, buf_hi, B, H, W, pitch, bstride, b, __float2int_rz(row[0]), __float2int_rz(row[1]),
-                __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm);
+                __float2int_rz(row[2]), __float2int_rz(row[3]), pad, dst + (int64_t)g * 3 * kS * kS, valid + g, sm, -1);
 }
 
 // Second launch of K5: the ROIs the first launch marked valid == 2 (crop area > kBigArea).  CTA (j, part)
@@ -579,6 +695,11 @@ __global__ void __launch_bounds__(kThreads, 2) roi_big_kernel(const uint8_t* __r
   __shared__ int wsum[kThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = count_ptr ? min(*count_ptr, N) : N;
+  {   // the common case: the fast path produced everything -- one pass over valid[], one barrier, done
+    int any = 0;
+    for (int g = tid; g < n; g += kThreads) any |= (valid[g] == 2);
+    if (!__syncthreads_or(any)) return;
+  }
   for (int j = blockIdx.x;; j += gridDim.x) {
     // locate the j-th deferred slot
     if (tid == 0) sm.sel[0] = -1;
@@ -707,8 +828,8 @@ extern "C" int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int
   cudaError_t e = cudaFuncSetAttribute(roi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
   if (e != cudaSuccess) return (int)e;
   const uint8_t* buf_hi = frames + (int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * pitch + (int64_t)W * 3;
-  roi_kernel<<<N, kFT, fsmem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride, boxes,
-                                                      batch_idx, roi_count, pad, dst, valid);
+  roi_kernel<<<N >= kSegMinRois ? 2 * N : N, kFT, fsmem, (cudaStream_t)stream>>>(frames, buf_hi, B, H, W, pitch, batch_stride,
+                                                                                boxes, batch_idx, roi_count, pad, dst, valid, N);
   e = cudaFuncSetAttribute(roi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   roi_big_kernel<<<dim3(kBigCtas, kBigParts), kThreads, smem, (cudaStream_t)stream>>>(

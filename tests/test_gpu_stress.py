@@ -34,8 +34,8 @@ def test_roi_random_boxes_odd_frames(cuda_dev):
     for (H, W) in [(701, 1001), (333, 517), (97, 2049)]:
         B, N = 2, 400
         frames = synth.synth_frames(B, H, W, seed=H)
-        w = 4 + torch.rand(N, generator=g) * min(260, W - 2)
-        h = 4 + torch.rand(N, generator=g) * min(260, H - 2)
+        w = 4 + torch.rand(N, generator=g) * min(340, W - 2)
+        h = 4 + torch.rand(N, generator=g) * min(340, H - 2)
         x1 = torch.rand(N, generator=g) * (W + 20) - 10 - w / 2
         y1 = torch.rand(N, generator=g) * (H + 20) - 10 - h / 2
         boxes = torch.stack((x1, y1, x1 + w, y1 + h), 1).float()
