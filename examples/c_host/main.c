@@ -68,7 +68,7 @@ int main(void) {
                           {d_head + 8000, (int64_t)NO * A, A, 20, 20, 32.f}};
   BK(b200yolo_class_filter(lv, 3, 1, NC, 0.25f, NULL, d_cand, d_canchor, d_ccount, CAP, st));
   BK(b200yolo_postprocess_small(lv, 3, d_cand, d_canchor, d_ccount, 1, CAP, 30000, 0.45, 7680.f, 0, MAXDET, d_scale, d_det,
-                                d_danchor, d_dcount, d_mask, NC, d_roicnt, st));
+                                d_danchor, d_dcount, d_mask, NC, d_roicnt, NULL, st));
   BK(b200yolo_roi_from_detections(d_frame, 1, H, W, (int64_t)W * 3, (int64_t)H * W * 3, d_det, d_dcount, d_roicnt, MAXDET, d_mask,
                                   NC, 6, 64, d_rois, d_rb, d_rd, d_valid, d_total, ROICAP, st));
   float det[MAXDET * 6], pad_px[4]; int n = 0, n_roi = 0;

@@ -47,6 +47,7 @@ enum {
 #define B200YOLO_MAX_LEVELS 3
 #define B200YOLO_MAX_CLASSES 4096
 #define B200YOLO_MAX_SORT 65536  /* candidates per image the sort/NMS kernels accept (cap) */
+#define B200YOLO_MAX_ANCHORS 65536 /* anchors per image: the sort key carries the anchor index in 16 bits */
 
 int b200yolo_version(void);
 const char* b200yolo_strerror(int code);
@@ -153,12 +154,16 @@ int b200yolo_nms(const float* cand, const int* cand_anchor, const int* cand_coun
  * rows come from b200yolo_class_filter; levels == NULL: rows already hold boxes), the K3 sort, the K4
  * NMS with max_det, optional scale_boxes, ROI counts.  Same outputs and bit-exact same results as
  * b200yolo_sort_topk + b200yolo_nms.  An image whose cand_count exceeds cap is processed on its first
- * cap slots only -- the caller must size cap for its confidence threshold and check cand_count. */
+ * cap slots only: the caller must detect it -- cand_seen[b] > cap -- and treat the image as failed (the
+ * Python host layer raises; SURVEY.md section 8(b): "raises rather than truncating silently").
+ * cand_seen: optional (B) int32.  When non-NULL the kernel copies the unclamped cand_count[b] into it and then
+ * RESETS cand_count[b] to 0 (cand_count is written in that case): the compaction counters are re-armed for the
+ * next step without a memset launch, and cand_seen is what the host reads back. */
 int b200yolo_postprocess_small(const b200yolo_level* levels, int n_levels, float* cand, const int* cand_anchor,
                                const int* cand_count, int B, int cap, int max_nms, double iou_thres,
                                float max_wh, int agnostic, int max_det, const float* scale, float* out,
                                int* out_anchor, int* out_count, const uint32_t* roi_class_mask, int roi_nc,
-                               int* roi_cnt, void* stream);
+                               int* roi_cnt, int* cand_seen, void* stream);
 
 /* ---- K2b+K3+K4 chained for the dense regime (cap > 1024; e.g. the conf = 0.001 evaluation setting) ----------
  * Input: the survivors of b200yolo_class_filter (scores, classes, anchors; boxes not decoded yet).  One host call
@@ -198,7 +203,8 @@ int b200yolo_roi_crop_resize(const uint8_t* frames, int B, int H, int W, int64_t
  * whose class is in class_mask; it is located on the device from det (B,max_det,6), det_count (B) and
  * the per-image counts roi_cnt (B) written by b200yolo_nms -- no selection launch, no host round trip
  * (the reference loops over detections on the host, detect.py:580-588).  dst: (roi_cap,3,size,size);
- * roi_batch / roi_det / valid: (roi_cap); roi_total: (1) = min(sum roi_cnt, roi_cap). */
+ * roi_batch / roi_det / valid: (roi_cap); roi_total: (1) = sum roi_cnt, NOT clamped: a value above roi_cap tells the
+ * caller that detections beyond the first roi_cap were not cropped (consumers use min(roi_total, roi_cap) rows). */
 int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H, int W, int64_t pitch,
                                  int64_t batch_stride, const float* det, const int* det_count,
                                  const int* roi_cnt, int max_det, const uint32_t* class_mask, int nc,
@@ -208,7 +214,8 @@ int b200yolo_roi_from_detections(const uint8_t* frames, int B, int H, int W, int
 /* Gather the detections of selected classes (the *_rank ids) into a dense ROI list, image-major,
  * detection order preserved: feeds K5 without a host round trip (detect.py:580-588 loop).
  * det: (B,max_det,6) from b200yolo_nms (source pixels); roi_boxes: (roi_cap,4); roi_batch:
- * (roi_cap); roi_det: (roi_cap) detection row index; roi_count: (1) MUST be zeroed by the caller. */
+ * (roi_cap); roi_det: (roi_cap) detection row index; roi_count: (1) = number of selected detections, NOT clamped
+ * (rows beyond roi_cap are dropped; the count tells). */
 int b200yolo_select_rois(const float* det, const int* det_count, int B, int max_det,
                          const uint32_t* class_mask, int nc, float* roi_boxes, int* roi_batch,
                          int* roi_det, int* roi_count, int roi_cap, void* stream);

@@ -36,7 +36,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_int, c_void_p]),
     "b200yolo_postprocess_small": (c_int, [POINTER(Level), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_double, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                           c_void_p, c_int, c_void_p, c_void_p]),
+                                           c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200yolo_postprocess_dense": (c_int, [POINTER(Level), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_double, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -204,11 +204,12 @@ class Candidates:
     cap: int
 
 
-def _alloc_candidates(B, cap, device, out: Optional[Candidates]):
+def _alloc_candidates(B, cap, device, out: Optional[Candidates], zero=True):
     if out is not None:
         if out.cap != cap or out.rows.shape[0] != B:
             raise ValueError("candidate buffers do not match (B, cap)")
-        out.count.zero_()
+        if zero:
+            out.count.zero_()
         return out
     return Candidates(torch.empty((B, cap, 6), dtype=torch.float32, device=device),
                       torch.empty((B, cap), dtype=torch.int32, device=device),
@@ -288,19 +289,20 @@ def _head_levels(head, strides, in_hw, level_hw, allow_pinned=False):
 
 
 def decode_and_filter(head, strides=(8, 16, 32), conf_thres=0.25, classes=None, in_hw=None, level_hw=None,
-                      cap=None, out: Optional[Candidates] = None, defer_boxes=False) -> Candidates:
+                      cap=None, out: Optional[Candidates] = None, defer_boxes=False, zero=True) -> Candidates:
     """Detect-head decode + confidence filter.
 
     ``head`` is either the concatenated (B, 64+nc, A) fp32 tensor (``Detect._inference``'s ``x_cat``;
     give ``in_hw`` = letterboxed input (h, w) or ``level_hw``) or the list of per-level
     (B, 64+nc, Hi, Wi) tensors straight from the Detect convolutions.  ``defer_boxes=True`` runs the
-    class filter only: the survivors' boxes are decoded later by ``postprocess_small``.
+    class filter only: the survivors' boxes are decoded later by ``postprocess_small``.  ``zero=False``: ``out.count``
+    is already zero (``postprocess_small(..., cand_seen=...)`` re-armed it): no memset launch.
     """
     if not 0 <= conf_thres <= 1:
         raise ValueError(f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0")
     levels, n_levels, B, nc, A, device, keep = _head_levels(head, strides, in_hw, level_hw)
     cap = int(cap or A)
-    cands = _alloc_candidates(B, cap, device, out)
+    cands = _alloc_candidates(B, cap, device, out, zero)
     mask = _class_mask(classes, nc, device)
     fn = _lib.load().b200yolo_class_filter if defer_boxes else _lib.load().b200yolo_decode_filter
     rc = fn(levels, n_levels, B, nc, float(conf_thres), _ptr(mask), _ptr(cands.rows), _ptr(cands.anchor),
@@ -312,12 +314,16 @@ def decode_and_filter(head, strides=(8, 16, 32), conf_thres=0.25, classes=None, 
 
 def postprocess_small(cands: Candidates, det: "Detections", head=None, strides=(8, 16, 32), in_hw=None, level_hw=None,
                       iou_thres=0.45, agnostic=False, max_nms=30000, max_wh=7680, scale: Optional[torch.Tensor] = None,
-                      roi_mask: Optional[torch.Tensor] = None, roi_nc=0, roi_cnt: Optional[torch.Tensor] = None):
+                      roi_mask: Optional[torch.Tensor] = None, roi_nc=0, roi_cnt: Optional[torch.Tensor] = None,
+                      cand_seen: Optional[torch.Tensor] = None):
     """Fused box decode + sort + NMS (+rescale) for ``cands.cap <= 1024``: one launch, one CTA per image.
 
     ``head``: the same head passed to ``decode_and_filter(..., defer_boxes=True)`` (None if the candidate
-    rows already hold boxes).  Results are bit-identical to ``nms_candidates``.  Images whose
-    ``cands.count`` exceeds ``cands.cap`` are processed on their first ``cap`` slots only: check the counts."""
+    rows already hold boxes).  Results are bit-identical to ``nms_candidates``.  An image whose candidate count
+    exceeds ``cands.cap`` is processed on its first ``cap`` slots only, which is NOT the reference's result: the
+    caller must check the counts (``Pipeline`` / ``HostRunner`` raise ``CandidateOverflow``).
+    ``cand_seen``: optional (B,) int32 -- receives the unclamped candidate counts while ``cands.count`` is reset to
+    zero inside the kernel, so the next ``decode_and_filter(..., out=cands, zero=False)`` needs no memset launch."""
     if not 0 <= iou_thres <= 1:
         raise ValueError(f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0")
     B = cands.rows.shape[0]
@@ -330,7 +336,7 @@ def postprocess_small(cands: Candidates, det: "Detections", head=None, strides=(
                                                 B, cands.cap, int(max_nms), float(iou_thres), float(max_wh),
                                                 int(bool(agnostic)), int(max_det), _ptr(scale), _ptr(det.rows),
                                                 _ptr(det.anchor), _ptr(det.count), _ptr(roi_mask), int(roi_nc),
-                                                _ptr(roi_cnt), _stream())
+                                                _ptr(roi_cnt), _ptr(cand_seen), _stream())
     _lib.check(rc, "postprocess_small")
     del keep
     return det
@@ -489,6 +495,8 @@ def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xyw
     if boxes.dim() != 2 or boxes.shape[1] < 4 or boxes.stride(1) != 1:
         raise ValueError("boxes must be (n, >=4) float32 with unit inner stride")
     gain, pad = geometry.scale_boxes_params(img1_shape, img0_shape, ratio_pad)
+    if boxes.shape[0] == 0:              # a frame without detections (upstream construct_result calls this on (0,4) views)
+        return boxes
     rc = _lib.load().b200yolo_scale_boxes(_ptr(boxes), boxes.shape[0], boxes.stride(0) if boxes.shape[0] else 4,
                                           float(gain), float(pad[0]), float(pad[1]), float(img0_shape[1]),
                                           float(img0_shape[0]), _stream())
@@ -539,7 +547,8 @@ def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=No
 def rois_from_detections(frames, det: Detections, roi_cnt, roi_mask, nc, roi_cap, pad=6, size=64, out=None):
     """Pipeline form of K5: crops + resizes every detection whose class is in ``roi_mask`` straight from
     the NMS output (``roi_cnt`` = per-image counts written by ``nms_sorted``).  Returns
-    (rois (roi_cap,3,size,size), roi_batch, roi_det, valid, roi_total (1,))."""
+    (rois (roi_cap,3,size,size), roi_batch, roi_det, valid, roi_total (1,)); ``roi_total`` is the number of detections
+    of the ROI classes in the batch, NOT clamped to ``roi_cap`` (only the first ``roi_cap`` are cropped)."""
     frames, _ = _frames_4d(frames, allow_pinned=True)     # pinned host frames: crops read zero-copy over PCIe
     B, H, W, _ = frames.shape
     max_det = det.rows.shape[1]
@@ -562,7 +571,8 @@ def rois_from_detections(frames, det: Detections, roi_cnt, roi_mask, nc, roi_cap
 def select_rois(det: Detections, classes, nc, roi_cap, out=None):
     """Device-side gather of the detections whose class is in ``classes`` (the ``*_rank`` ids).
 
-    Returns (roi_boxes (cap,4) f32, roi_batch (cap,) i32, roi_det (cap,) i32, roi_count (1,) i32)."""
+    Returns (roi_boxes (cap,4) f32, roi_batch (cap,) i32, roi_det (cap,) i32, roi_count (1,) i32); ``roi_count`` is not
+    clamped to ``roi_cap`` (rows beyond it are dropped)."""
     B, max_det, _ = det.rows.shape
     dev = det.rows.device
     mask = _class_mask(classes, nc, dev)

@@ -525,7 +525,7 @@ extern "C" int b200yolo_filter_decoded(const float* pred, int B, int channels, i
                                        int* cand_count, int cap, void* stream) {
   B200_REQUIRE(pred && cand && cand_anchor && cand_count, B200YOLO_ERR_NULL);
   B200_REQUIRE(B > 0 && B <= 65535 && nc > 0 && A > 0 && cap > 0 && channels >= 4 + nc, B200YOLO_ERR_SHAPE);
-  B200_REQUIRE(nc <= B200YOLO_MAX_CLASSES, B200YOLO_ERR_UNSUPPORTED);
+  B200_REQUIRE(nc <= B200YOLO_MAX_CLASSES && A <= B200YOLO_MAX_ANCHORS, B200YOLO_ERR_UNSUPPORTED);
   B200_REQUIRE(conf_thres >= 0.f && conf_thres <= 1.f, B200YOLO_ERR_RANGE);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(pred) & 3) == 0, B200YOLO_ERR_ALIGN);
   Levels L;

@@ -35,7 +35,9 @@ static inline int build_levels(const b200yolo_level* levels, int n_levels, Level
       L.ptr[l] = nullptr; L.bstride[l] = 0; L.cstride[l] = 0; L.w[l] = 1; L.stride[l] = 1.f; L.off[l] = (int)off;
     }
   }
-  B200_REQUIRE(off <= (1LL << 30), B200YOLO_ERR_UNSUPPORTED);
+  // the sort key carries the anchor index in 16 bits (nms_common.cuh make_key): more anchors than that would break
+  // the anchor-order tie rule and the uniqueness of keys the select-sort relies on
+  B200_REQUIRE(off <= B200YOLO_MAX_ANCHORS, B200YOLO_ERR_UNSUPPORTED);
   for (int l = n_levels; l <= B200YOLO_MAX_LEVELS; ++l) L.off[l] = (int)off;
   return B200YOLO_OK;
 }

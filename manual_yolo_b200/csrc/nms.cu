@@ -328,9 +328,10 @@ extern "C" int b200yolo_postprocess_dense(const b200yolo_level* levels, int n_le
 
 extern "C" int b200yolo_scale_boxes(float* boxes, int n, int row_stride, float gain, float pad_x, float pad_y,
                                     float w0, float h0, void* stream) {
+  B200_REQUIRE(n >= 0 && gain > 0.f, B200YOLO_ERR_SHAPE);
+  if (n == 0) return B200YOLO_OK;           // an empty tensor has a NULL data pointer: nothing to do, not an error
   B200_REQUIRE(boxes, B200YOLO_ERR_NULL);
-  B200_REQUIRE(n >= 0 && row_stride >= 4 && gain > 0.f, B200YOLO_ERR_SHAPE);
-  if (n == 0) return B200YOLO_OK;
+  B200_REQUIRE(row_stride >= 4, B200YOLO_ERR_SHAPE);
   scale_boxes_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boxes, n, row_stride, gain, pad_x, pad_y,
                                                                         w0, h0);
   return b200_launch_status();

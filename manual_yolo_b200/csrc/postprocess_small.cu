@@ -57,12 +57,21 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
                                                                const float* __restrict__ scale, float* __restrict__ out,
                                                                int* __restrict__ out_anchor, int* __restrict__ out_count,
                                                                const uint32_t* __restrict__ roi_mask, int roi_nc,
-                                                               int* __restrict__ roi_cnt) {
+                                                               int* __restrict__ roi_cnt, int* __restrict__ cand_seen,
+                                                               int* __restrict__ cand_count_rw) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   int* keep = reinterpret_cast<int*>(smem_raw + ((sizeof(Smem) + 15) & ~(size_t)15));   // [max_det]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = min(cand_count[b], cap);
+  const int n_seen = cand_count[b];
+  const int n = min(n_seen, cap);
+  __syncthreads();                          // every thread has read the count before thread 0 may reset it
+  if (cand_seen != nullptr && tid == 0) {
+    // hand the (unclamped) candidate count to the caller and re-arm the compaction counter for the next step: no
+    // memset launch is needed between steps, and n_seen > cap tells the host that this image overflowed
+    cand_seen[b] = n_seen;
+    cand_count_rw[b] = 0;
+  }
   if (n <= 0) {
     if (tid == 0) { out_count[b] = 0; if (roi_cnt) roi_cnt[b] = 0; }
     return;
@@ -309,8 +318,10 @@ extern "C" int b200yolo_postprocess_small(const b200yolo_level* levels, int n_le
                                           const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
                                           double iou_thres, float max_wh, int agnostic, int max_det,
                                           const float* scale, float* out, int* out_anchor, int* out_count,
-                                          const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* stream) {
+                                          const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, int* cand_seen,
+                                          void* stream) {
   B200_REQUIRE(cand && cand_anchor && cand_count && out && out_anchor && out_count, B200YOLO_ERR_NULL);
+  B200_REQUIRE(cand_seen != cand_count, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(B > 0 && cap > 0 && max_nms > 0 && max_det > 0, B200YOLO_ERR_SHAPE);
   B200_REQUIRE(cap <= kCapMax && max_det <= 4096, B200YOLO_ERR_UNSUPPORTED);
   B200_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, B200YOLO_ERR_RANGE);
@@ -332,6 +343,7 @@ extern "C" int b200yolo_postprocess_small(const b200yolo_level* levels, int n_le
   if (e != cudaSuccess) return (int)e;
   postprocess_small_kernel<<<B, NT, smem, (cudaStream_t)stream>>>(L, decode, cand, cand_anchor, cand_count, cap, max_nms,
                                                                   iou_thres, max_wh, agnostic, max_det, scale, out,
-                                                                  out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt);
+                                                                  out_anchor, out_count, roi_class_mask, roi_nc, roi_cnt,
+                                                                  cand_seen, const_cast<int*>(cand_count));
   return b200_launch_status();
 }

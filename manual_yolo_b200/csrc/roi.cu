@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(kFT, 6) roi_det_kernel(const uint8_t* __restri
       }
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (g == 0 && lane == 0) *roi_total = min(carry, roi_cap);
+    if (g == 0 && lane == 0) *roi_total = carry;      // not clamped: > roi_cap tells the host that ROIs were dropped
     // ---- (2) the selk-th allowed detection of image selb, in kept (score) order ----
     int seli = -1;
     if (selb >= 0) {
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(1024) select_rois_kernel(const float* __restri
     carry = warp_tot[0];
     __syncthreads();
   }
-  if (tid == 0) *roi_count = min(carry, roi_cap);
+  if (tid == 0) *roi_count = carry;                 // not clamped: > roi_cap tells the host that ROIs were dropped
   // pass 2: ordered scatter
   for (int b = wid; b < B; b += 32) {
     const int n = min(det_count[b], max_det);

@@ -165,14 +165,20 @@ def rank_text_from_top1(pred_name: str, top1conf: float, det_class_name: str = "
     return ""
 
 
-def classify_rank_rois(result, forward_logits, rank_names: dict, det_names: Optional[dict] = None) -> List[dict]:
+def classify_rank_rois(result, forward_logits, rank_names: Optional[dict] = None,
+                       det_names: Optional[dict] = None) -> List[dict]:
     """Batched form of the reference's per-crop loop (``detect.py:580-588`` -> ``:121-131``): ONE forward of the
     rank classifier over the K5 batch of a step (``result``: a ``PipelineResult``), one device->host read of
     (top1, top1conf), then the reference's thresholds and text clean-up.  ``forward_logits``: callable mapping the
-    (n,3,64,64) fp32 ROI tensor to (n,13) logits (the YOLOv8n-cls network stays torch).  Returns one dict per valid
-    ROI: frame, det (row in that frame's detections), class_id, top1, top1conf, text."""
-    import torch
-    n = int(result.roi_count)
+    (n,3,64,64) fp32 ROI tensor to (n,13) logits (the YOLOv8n-cls network stays torch) -- e.g. a
+    ``classifier.RankClassifier`` from ``classifier.load_rank_classifier("rank_classifier.pt")`` (``detect.py:21``),
+    whose ``names`` are used when ``rank_names`` is not given.  Returns one dict per valid ROI: frame, det (row in that
+    frame's detections), class_id, top1, top1conf, text."""
+    if rank_names is None:
+        rank_names = getattr(forward_logits, "names", None)
+        if rank_names is None:
+            raise ValueError("rank_names is required when the classifier carries no names")
+    n = min(int(result.roi_count), int(result.rois.shape[0]))
     if n == 0:
         return []
     probs = forward_logits(result.rois[:n]).softmax(1)

@@ -77,6 +77,16 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def max_over_ranks_list(values, device=None):
+    """Element-wise max of a per-rank list of scalars (per-block elapsed times) over the job."""
+    if not dist.is_initialized():
+        return [float(v) for v in values]
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
 def sum_over_ranks(value: float, device=None) -> float:
     if not dist.is_initialized():
         return float(value)
@@ -84,6 +94,56 @@ def sum_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+DET_DTYPE = [("frame", "<i4"), ("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4"), ("conf", "<f4"), ("class_id", "<i4")]
+
+
+def detections_columnar(det_rows, det_count, frame_offset: int = 0):
+    """Padded NMS output of a batch (host tensors / arrays: rows (B,max_det,6), counts (B,)) -> one numpy structured
+    array with a row per detection (``DET_DTYPE``), vectorised: no Python object per detection.  This is the
+    hand-off format of the host-side gather (the reference appends one dict per detection and re-dumps the whole
+    history every frame, ``/root/reference/detect.py:590-598, 679-690``)."""
+    import numpy as np
+    rows = np.asarray(det_rows, dtype=np.float32)
+    cnt = np.asarray(det_count, dtype=np.int64)
+    B, max_det = rows.shape[0], rows.shape[1]
+    keep = np.arange(max_det)[None, :] < np.minimum(cnt, max_det)[:, None]
+    sel = rows[keep]
+    out = np.empty(sel.shape[0], dtype=DET_DTYPE)
+    out["frame"] = np.repeat(np.arange(B, dtype=np.int32) + frame_offset, keep.sum(1))
+    for k, name in enumerate(("x1", "y1", "x2", "y2", "conf")):
+        out[name] = sel[:, k]
+    out["class_id"] = sel[:, 5].astype(np.int32)
+    return out
+
+
+def columnar_to_records(arr, names=None):
+    """Structured detections -> the reference's ``frame_data`` dicts (``detect.py:590-598``; bbox ``int()``-truncated as
+    ``detect.py:581``, conf rounded to 3 places) -- only for the JSON that is actually written."""
+    recs = []
+    for r in arr:
+        cid = int(r["class_id"])
+        recs.append({"frame": int(r["frame"]), "tracker_id": -1, "class_id": cid,
+                     "class_name": names.get(cid, f"class{cid}") if names else f"class{cid}",
+                     "bbox": [int(r["x1"]), int(r["y1"]), int(r["x2"]), int(r["y2"])], "conf": round(float(r["conf"]), 3)})
+    return recs
+
+
+def gather_columnar(arr, dst: int = 0):
+    """Host-side gather of per-rank structured detection arrays to rank ``dst`` (frame indices are global, so the
+    merged array is sorted by frame).  One pickled numpy buffer per rank: O(bytes), not O(detections) Python objects.
+    Returns the merged array on ``dst`` and None elsewhere."""
+    import numpy as np
+    if not dist.is_initialized():
+        return arr[np.argsort(arr["frame"], kind="stable")]
+    world = dist.get_world_size()
+    out = [None] * world if dist.get_rank() == dst else None
+    dist.gather_object(arr, out, dst=dst)
+    if dist.get_rank() != dst:
+        return None
+    merged = np.concatenate(out)
+    return merged[np.argsort(merged["frame"], kind="stable")]
 
 
 def gather_records(records: List[dict], dst: int = 0):

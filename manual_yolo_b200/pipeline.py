@@ -7,7 +7,8 @@ preprocessing (``detect.py:121``).  The backbone/neck stay torch modules outside
 Detect-head tensor is an input here (``head``), the letterboxed network input an output (``net_in``).
 
 All buffers are allocated once in ``__init__`` (the C ABI never allocates); a step is 5 launches of this
-package's kernels in the sparse regime (7-10 on the general / dense path) plus one counter memset, capturable
+package's kernels in the sparse regime and nothing else (the fused post-processing kernel re-arms the compaction
+counters itself: no memset node), 7-10 launches plus one counter memset on the general / dense path; capturable
 into one CUDA graph.
 """
 
@@ -24,6 +25,32 @@ RANK_CLASS_IDS = (6, 11, 16, 21, 26, 37, 43)  # *_rank classes, roadmap1.v3i.yol
 FUSED_CAP_MAX = 1024                           # b200yolo_postprocess_small envelope
 
 
+class CapacityOverflow(RuntimeError):
+    """A fixed-capacity buffer of the step was too small for its input: the results of the step are NOT the
+    reference's and must not be used (raise rather than truncate silently)."""
+
+
+class CandidateOverflow(CapacityOverflow):
+    """More candidates passed the confidence threshold in one image than ``cap`` slots exist."""
+
+
+class RoiOverflow(CapacityOverflow):
+    """More detections of the ROI classes in the batch than ``roi_cap`` crops exist."""
+
+
+def check_counts(cand_count, cap, roi_total=None, roi_cap=None):
+    """Host-side capacity check on counts that were already copied back (no extra device sync): raises
+    ``CandidateOverflow`` / ``RoiOverflow``.  Returns the largest per-image candidate count."""
+    mx = int(cand_count.max()) if cand_count.numel() else 0
+    if mx > cap:
+        raise CandidateOverflow(f"candidate overflow: {mx} candidates in one image > cap={cap}; the step's detections are "
+                                "invalid -- raise cap (cap=None uses all anchors) or the confidence threshold")
+    if roi_total is not None and roi_cap is not None and int(roi_total) > roi_cap:
+        raise RoiOverflow(f"ROI overflow: {int(roi_total)} detections of the ROI classes in the batch > roi_cap={roi_cap}; "
+                          "raise rois_per_frame")
+    return mx
+
+
 @dataclass
 class PipelineResult:
     net_in: torch.Tensor        # (B,3,h,w) f32 letterboxed + normalised network input (K1)
@@ -33,7 +60,18 @@ class PipelineResult:
     roi_batch: torch.Tensor     # (roi_cap,) i32 frame index of each ROI
     roi_det: torch.Tensor       # (roi_cap,) i32 detection row of each ROI
     roi_valid: torch.Tensor     # (roi_cap,) i32
-    roi_count: torch.Tensor     # (1,) i32
+    roi_count: torch.Tensor     # (1,) i32: ROI-class detections in the batch (NOT clamped: > roi_cap = overflow)
+    cap: int = 0                # candidate slots per image (cand_count[b] > cap = overflow: results invalid)
+
+    def n_rois(self) -> int:
+        """Valid rows of ``rois`` (one device->host read)."""
+        return min(int(self.roi_count), int(self.rois.shape[0]))
+
+    def check_overflow(self) -> int:
+        """Raise ``CandidateOverflow`` / ``RoiOverflow`` if a capacity was exceeded in this step (device->host read of
+        the counts).  Returns the largest per-image candidate count."""
+        return check_counts(self.cand_count.cpu(), self.cap if self.cap > 0 else 1 << 30, self.roi_count.cpu(),
+                            int(self.rois.shape[0]))
 
 
 class Pipeline:
@@ -69,6 +107,10 @@ class Pipeline:
         self.cls_mask = api._class_mask(classes, self.nc, dev)
         self.roi_mask = api._class_mask(self.roi_classes, self.nc, dev)
         self.roi_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+        # fused path: the post-processing kernel hands the per-image candidate counts out here and re-arms
+        # cands.count itself, so a step has no memset launch
+        self.cand_seen = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.nvtx = False                            # NVTX range per stage (nsys / ncu --nvtx), see _tick
         self.roi_out = (torch.zeros((self.roi_cap, 3, roi_size, roi_size), dtype=torch.float32, device=dev),
                         torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
                         torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
@@ -140,12 +182,13 @@ class Pipeline:
             # sparse regime (cap <= 1024): class filter, then ONE fused launch for decode + sort + NMS
             t("decode_filter")
             api.decode_and_filter(head, self.strides, self.conf, self.cls_mask, level_hw=self.level_hw,
-                                  cap=self.cap, out=self.cands, defer_boxes=True)
+                                  cap=self.cap, out=self.cands, defer_boxes=True, zero=False)
             t("postprocess_small")
             det = api.postprocess_small(self.cands, self.ws.det, self._dfl_head, self.strides, level_hw=self.level_hw,
                                         iou_thres=self.iou, agnostic=self.agnostic, max_nms=self.max_nms,
                                         max_wh=self.max_wh, scale=self.scale, roi_mask=self.roi_mask, roi_nc=self.nc,
-                                        roi_cnt=self.roi_cnt)
+                                        roi_cnt=self.roi_cnt, cand_seen=self.cand_seen)
+            cand_count = self.cand_seen
         else:
             # general / dense regime: class filter, then ONE host call for select-sort -> decode of the ordered
             # prefix -> windowed NMS (+ exact fallback)
@@ -157,11 +200,12 @@ class Pipeline:
                                         iou_thres=self.iou, agnostic=self.agnostic, max_det=self.max_det,
                                         max_nms=self.max_nms, max_wh=self.max_wh, scale=self.scale,
                                         roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
+            cand_count = self.cands.count
         t("roi_crop_resize")
         ro = api.rois_from_detections(self._roi_frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
         t(None)
-        return PipelineResult(self.net_in, det, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
+        return PipelineResult(self.net_in, det, cand_count, ro[0], ro[1], ro[2], ro[3], ro[4], self.cap)
 
     # -- per-kernel CUDA-event timing (bench.py): events on the launching stream around each stage --
     def enable_profiling(self, on=True, external=False):
@@ -172,6 +216,12 @@ class Pipeline:
         self._prof_external = bool(external)
 
     def _tick(self, name):
+        if getattr(self, "nvtx", False):             # one NVTX range per stage (tracing hooks)
+            if getattr(self, "_nvtx_open", False):
+                torch.cuda.nvtx.range_pop()
+            self._nvtx_open = name is not None
+            if name is not None:
+                torch.cuda.nvtx.range_push(f"b200yolo:{name}")
         if getattr(self, "_prof", None) is None:
             return
         ev = torch.cuda.Event(enable_timing=True, external=getattr(self, "_prof_external", False))
@@ -188,9 +238,10 @@ class Pipeline:
         return out
 
     # -- CUDA-graph form: one launch per batch ---------------------------------------------------
-    def capture(self, frames: torch.Tensor, head: torch.Tensor):
-        """Capture one step on static input buffers; afterwards ``replay()`` re-runs it (copy new data
-        into the tensors passed here first)."""
+    def capture(self, frames: torch.Tensor, head: torch.Tensor, key=0):
+        """Capture one step on static input buffers; afterwards ``replay(key)`` re-runs it (copy new data into the
+        tensors passed here first).  Several graphs can be captured on one ``Pipeline`` (one per ``key``: e.g. one per
+        resident input batch of a stream): they share the output buffers, so replay them one after another."""
         self._static = (frames, head)
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
@@ -200,16 +251,24 @@ class Pipeline:
         torch.cuda.synchronize()
         if self._prof is not None:
             self._prof, self._open = [], None        # keep only the events recorded inside the graph
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._result = self(frames, head)
-        return self._result
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            result = self(frames, head)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self._graphs[key] = (graph, result)
+        self._graph, self._result = graph, result
+        return result
 
-    def replay(self) -> PipelineResult:
+    def replay(self, key=None) -> PipelineResult:
         if self._graph is None:
             raise RuntimeError("capture() first")
-        self._graph.replay()
-        return self._result
+        if key is None:
+            self._graph.replay()
+            return self._result
+        graph, result = self._graphs[key]
+        graph.replay()
+        return result
 
     # -- host-facing entry: pinned host buffers in, host results out -----------------------------
     def run_host(self, frames_host: torch.Tensor, head_host: torch.Tensor, staging=None):
@@ -217,13 +276,16 @@ class Pipeline:
         path, D2H of detections/counts.  Returns (det_rows, det_count, roi_count) host tensors."""
         if staging is None:
             staging = self.make_staging()
-        d_frames, d_head, h_rows, h_count, h_roi = staging
+        d_frames, d_head, h_rows, h_count, h_roi, h_cand = staging
         d_frames.copy_(frames_host, non_blocking=True)
         d_head.copy_(head_host, non_blocking=True)
         res = self(d_frames, d_head)
         h_rows.copy_(res.det.rows, non_blocking=True)
         h_count.copy_(res.det.count, non_blocking=True)
         h_roi.copy_(res.roi_count, non_blocking=True)
+        h_cand.copy_(res.cand_count, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # host results are complete when this returns ...
+        check_counts(h_cand, self.cap, h_roi, self.roi_cap)   # ... and valid: raises on capacity overflow
         return h_rows, h_count, h_roi
 
     def launches_per_step(self):
@@ -232,13 +294,11 @@ class Pipeline:
         return 5 if self.fused else (10 if self.cap > 2048 else 7)
 
     def check_overflow(self):
-        """Raise if any image of the last step had more candidates than ``cap`` (one D2H of the counts).
-        With ``cap < A`` a candidate beyond ``cap`` is dropped, so results are only valid when this passes."""
-        mx = int(self.cands.count.max())
-        if mx > self.cap:
-            raise RuntimeError(f"candidate overflow: {mx} candidates in one image > cap={self.cap}; "
-                               "raise cap (cap=None uses all anchors) or the confidence threshold")
-        return mx
+        """Raise ``CandidateOverflow`` / ``RoiOverflow`` if the last step exceeded a capacity (one D2H of the counts).
+        With ``cap < A`` a candidate beyond ``cap`` is dropped, so results are only valid when this passes.
+        ``run_host`` / ``HostRunner`` perform this check themselves on the counts they read back anyway."""
+        cc = self.cand_seen if self.fused else self.cands.count
+        return check_counts(cc.cpu(), self.cap, self.roi_out[4].cpu(), self.roi_cap)
 
     def make_staging(self, rows_only=False, head=True):
         dev = self.device
@@ -248,13 +308,14 @@ class Pipeline:
                 torch.zeros((self.B, no, self.A), dtype=torch.float32, device=dev) if head else None,
                 torch.empty((self.B, self.max_det, 6), dtype=torch.float32).pin_memory(),
                 torch.empty((self.B,), dtype=torch.int32).pin_memory(),
-                torch.empty((1,), dtype=torch.int32).pin_memory())
+                torch.empty((1,), dtype=torch.int32).pin_memory(),
+                torch.zeros((self.B,), dtype=torch.int32).pin_memory())
 
     def h2d_bytes_per_step(self):
         return self.B * self.src_hw[0] * self.src_hw[1] * 3 + self.B * (64 + self.nc) * self.A * 4
 
     def d2h_bytes_per_step(self):
-        return self.B * self.max_det * 6 * 4 + self.B * 4 + 4
+        return self.B * self.max_det * 6 * 4 + 2 * self.B * 4 + 4       # detections, det counts, candidate counts, ROI total
 
 
 class HostRunner:
@@ -289,9 +350,15 @@ class HostRunner:
         self.step = 0
 
     def submit(self, frames_host: torch.Tensor, head_host: torch.Tensor):
-        """Enqueue one step; returns the (rows, count, roi_count) pinned host tensors it will fill."""
+        """Enqueue one step; returns the (rows, count, roi_count) pinned host tensors it will fill.  Before a staging
+        slot is re-used the counts of the step that last used it are checked (they are complete by then: the copy
+        stream waits on that step): a capacity overflow raises ``CandidateOverflow`` / ``RoiOverflow`` here, at the
+        latest in ``wait()``."""
         s = self.step % self.depth
-        d_frames, d_head, h_rows, h_count, h_roi = self.staging[s]
+        if self.step >= self.depth:
+            self.free[s].synchronize()
+            self._check(s)
+        d_frames, d_head, h_rows, h_count, h_roi, h_cand = self.staging[s]
         p = self.pipe
         compute = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
@@ -315,14 +382,21 @@ class HostRunner:
         h_rows.copy_(res.det.rows, non_blocking=True)
         h_count.copy_(res.det.count, non_blocking=True)
         h_roi.copy_(res.roi_count, non_blocking=True)
+        h_cand.copy_(res.cand_count, non_blocking=True)
         self.free[s].record(compute)
         self.step += 1
         return h_rows, h_count, h_roi
 
+    def _check(self, s):
+        st = self.staging[s]
+        check_counts(st[5], self.pipe.cap, st[4], self.pipe.roi_cap)
+
     def wait(self, slot=None):
-        """Block until the step last submitted into ``slot`` (default: the most recent) has finished."""
+        """Block until the step last submitted into ``slot`` (default: the most recent) has finished; raises
+        ``CandidateOverflow`` / ``RoiOverflow`` if that step exceeded a capacity (its results are invalid)."""
         s = (self.step - 1) % self.depth if slot is None else slot
         self.free[s].synchronize()
+        self._check(s)
 
     def h2d_bytes_per_step(self):
         """Bytes moved by the H2D DMAs of a step (zero-copy reads are extra: see ``zero_copy_bytes``)."""
@@ -367,18 +441,22 @@ class BatchStream:
         self.step = 0
 
     def capture(self, inputs):
-        """``inputs``: one (frames, head) pair of static device tensors per slot (may be the same pair)."""
+        """``inputs``: per slot, one (frames, head) pair of static device tensors (may be the same pair for every slot)
+        or a list of such pairs -- the resident batches that slot will process, graph ``k`` = its k-th pair."""
         if len(inputs) != self.depth:
-            raise ValueError("one (frames, head) pair per slot")
-        for p, (f, h) in zip(self.pipes, inputs):
-            p.capture(f, h)
+            raise ValueError("one (frames, head) pair (or list of pairs) per slot")
+        for p, item in zip(self.pipes, inputs):
+            pairs = item if isinstance(item, list) else [item]
+            for k, (f, h) in enumerate(pairs):
+                p.capture(f, h, key=k)
 
-    def submit(self) -> PipelineResult:
+    def submit(self, key=None) -> PipelineResult:
+        """Replay the next slot's graph (``key``: which of that slot's captured batches) on the slot's stream."""
         s = self.step % self.depth
         st = self.streams[s]
         st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
-            res = self.pipes[s].replay()
+            res = self.pipes[s].replay(key)
         self.step += 1
         return res
 
@@ -387,6 +465,12 @@ class BatchStream:
         cur = torch.cuda.current_stream()
         for st in self.streams:
             cur.wait_stream(st)
+
+    def check_overflow(self):
+        """Synchronise every slot and raise ``CandidateOverflow`` / ``RoiOverflow`` if its last batch exceeded a capacity."""
+        for st, p in zip(self.streams, self.pipes):
+            st.synchronize()
+            p.check_overflow()
 
 
 class SlicedPipeline:
@@ -438,6 +522,7 @@ class SlicedPipeline:
         self.roi_cap = max(1, self.F * int(rois_per_frame))
         self.roi_mask = api._class_mask(self.roi_classes, self.nc, dev)
         self.roi_cnt = torch.zeros((self.F,), dtype=torch.int32, device=dev)
+        self.cand_seen = torch.zeros((n_items,), dtype=torch.int32, device=dev)
         self.roi_out = (torch.zeros((self.roi_cap, 3, roi_size, roi_size), dtype=torch.float32, device=dev),
                         torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
                         torch.zeros((self.roi_cap,), dtype=torch.int32, device=dev),
@@ -457,15 +542,17 @@ class SlicedPipeline:
         self.preprocess(frames)
         if self.fused:
             api.decode_and_filter(head, self.strides, self.conf, level_hw=self.level_hw, cap=self.cap, out=self.cands,
-                                  defer_boxes=True)
+                                  defer_boxes=True, zero=False)
             det = api.postprocess_small(self.cands, self.ws.det, head, self.strides, level_hw=self.level_hw,
                                         iou_thres=self.iou, agnostic=self.agnostic, max_nms=self.max_nms,
-                                        max_wh=self.max_wh, scale=self.scale)
+                                        max_wh=self.max_wh, scale=self.scale, cand_seen=self.cand_seen)
+            cand_count = self.cand_seen
         else:
             api.decode_and_filter(head, self.strides, self.conf, level_hw=self.level_hw, cap=self.cap, out=self.cands)
             api.sort_candidates(self.cands, self.max_nms, self.ws)
             det = api.nms_sorted(self.cands, self.ws, self.iou, self.agnostic, self.max_det, self.max_nms, self.max_wh,
                                  scale=self.scale)
+            cand_count = self.cands.count
         self.slice_det = det
         api.gather_slice_detections(det, self.slices, self.F, out=self.mcands)
         api.sort_candidates(self.mcands, self.max_nms, self.mws)
@@ -473,13 +560,12 @@ class SlicedPipeline:
                                 self.max_wh, roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
         ro = api.rois_from_detections(frames, merged, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
-        return PipelineResult(self.net_in, merged, self.cands.count, ro[0], ro[1], ro[2], ro[3], ro[4])
+        return PipelineResult(self.net_in, merged, cand_count, ro[0], ro[1], ro[2], ro[3], ro[4], self.cap)
 
     def check_overflow(self):
-        mx = int(self.cands.count.max())
-        if mx > self.cap:
-            raise RuntimeError(f"candidate overflow: {mx} candidates in one slice > cap={self.cap}")
-        return mx
+        """Raise ``CandidateOverflow`` / ``RoiOverflow`` if the last call exceeded a capacity (one D2H of the counts)."""
+        cc = self.cand_seen if self.fused else self.cands.count
+        return check_counts(cc.cpu(), self.cap, self.roi_out[4].cpu(), self.roi_cap)
 
 
 def detections_to_records(det_rows, det_count, names=None, frame_offset=0):

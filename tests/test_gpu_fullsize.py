@@ -72,9 +72,9 @@ def test_config2_full_batch_properties(cuda_dev):
     assert bool((inner == torch.tensor(77, dtype=torch.float32).div(255).item()).all())
     assert float(r1.net_in.min()) >= 0.0 and float(r1.net_in.max()) <= 1.0
     # ROI stage: as many ROIs as rank-class detections, image-major; the constant frame gives constant crops
-    n = int(r1.roi_count)
+    n = r1.n_rois()
     want = sum(int(c) in m.pipeline.RANK_CLASS_IDS for b, k in enumerate(counts) for c in rows[b, :k, 5].tolist())
-    assert n == min(want, fused.roi_cap) and n > 100
+    assert int(r1.roi_count) == want and n == min(want, fused.roi_cap) and n > 100      # roi_count is not clamped
     rb = r1.roi_batch[:n].cpu()
     assert bool((rb[:-1] <= rb[1:]).all()) and set(r1.roi_valid[:n].cpu().tolist()) <= {1, 2}
     for i in (rb == 1).nonzero().view(-1).tolist():
@@ -141,3 +141,67 @@ def test_config4_full_batch_properties(cuda_dev):
     # the same boxes read zero-copy from pinned host frames give the same bytes
     out2, valid2 = m.crop_resize_rois(frames.pin_memory(), boxes.to(cuda_dev), bidx.to(cuda_dev), pad=6)
     assert torch.equal(out2, out) and torch.equal(valid2, valid)
+
+
+def _oracle_vs_det(det, head_cpu, lv, conf, iou, images, in_hw=None, src_hw=None, max_det=300):
+    """Kept anchor indices + class ids bit-exact, boxes/scores <= 1e-4 against the CPU oracle for the given images."""
+    from oracle import head as ohead
+    from oracle import nms as onms
+    pred = ohead.detect_inference_ref(head_cpu[images], lv)
+    out, idx = onms.non_max_suppression_ref(pred, conf, iou, max_det=max_det, return_idxs=True)
+    worst = 0.0
+    for j, b in enumerate(images):
+        k = int(det.count[b])
+        assert k == out[j].shape[0], (b, k, out[j].shape)
+        assert torch.equal(det.anchor[b, :k].cpu().long(), idx[j]), b                # kept sets, in order
+        got, exp = det.rows[b, :k].cpu(), out[j].clone()
+        if src_hw is not None:
+            exp[:, :4] = oboxes.scale_boxes_ref(in_hw, exp[:, :4], src_hw)
+        assert torch.equal(got[:, 5], exp[:, 5]), b                                  # class ids
+        if k:
+            worst = max(worst, float((got[:, :5] - exp[:, :5]).abs().max()))
+    assert worst <= 1e-4, worst
+    return worst
+
+
+def test_config2_bench_batch_equals_oracle_all_64_frames(cuda_dev):
+    """The EXACT batch bench.py times (seed 0, 64 frames of 1920x1200, label-derived head, conf 0.25, iou 0.45) against the
+    CPU oracle for every frame: letterbox bit-exact, kept sets / class ids bit-exact, boxes + scores <= 1e-4, every ROI
+    <= 1/255 (observed 0)."""
+    from oracle import letterbox as olb
+    B, nc, src_hw, conf, iou = 64, 64, (1200, 1920), 0.25, 0.45
+    frames = synth.synth_frames(B, *src_hw, seed=0)
+    pipe = m.Pipeline(B, src_hw, nc, conf=conf, iou=iou, device=cuda_dev, cap=1024)
+    head, _ = synth.synth_head_from_labels(B, nc, in_hw=pipe.in_hw, src_hw=src_hw, seed=0, conf_thres=conf)
+    res = pipe(frames.to(cuda_dev), head.to(cuda_dev))
+    torch.cuda.synchronize()
+    assert pipe.check_overflow() <= pipe.cap
+    for b0 in range(0, B, 16):
+        ref = olb.preprocess_ref(list(frames[b0:b0 + 16].numpy()), (640, 640))
+        assert torch.equal(res.net_in[b0:b0 + 16].cpu(), ref)
+    _oracle_vs_det(res.det, head, pipe.level_hw, conf, iou, list(range(B)), in_hw=pipe.in_hw, src_hw=src_hw)
+    n = res.n_rois()
+    rb, rd = res.roi_batch[:n].cpu().tolist(), res.roi_det[:n].cpu().tolist()
+    rows = res.det.rows.cpu()
+    want = [(b, i) for b in range(B) for i in range(int(res.det.count[b])) if int(rows[b, i, 5]) in m.pipeline.RANK_CLASS_IDS]
+    assert list(zip(rb, rd)) == want[:pipe.roi_cap] and int(res.roi_count) == len(want) and n == min(len(want), pipe.roi_cap) and n > 100
+    rois = res.rois[:n].cpu()
+    for g, (b, i) in enumerate(zip(rb, rd)):
+        crop = oboxes.safe_crop_ref(frames[b].numpy(), *[int(v) for v in rows[b, i, :4]], pad=6)
+        assert crop is not None and torch.equal(rois[g], oroi.classify_preprocess_ref(crop)), (g, b, i)
+
+
+@pytest.mark.parametrize("iou", [0.7, 0.45])
+def test_config3_full_batch_oracle_subsample_of_16(cuda_dev, iou):
+    """configs[2] at its full size (256 x 144 x 8400, conf 0.001): 16 images drawn from the whole batch (every seed
+    block, incl. the adversarial columns) equal the CPU oracle -- kept anchors + class ids bit-exact, boxes/scores 1e-4."""
+    B, nc, conf = 256, 80, 0.001
+    lv = geometry.level_shapes(640, 640)
+    head_cpu = torch.cat([synth.synth_head_dense(64, nc, seed=s) for s in range(B // 64)])
+    head = head_cpu.to(cuda_dev)
+    cands = m.decode_and_filter(head, conf_thres=conf, level_hw=lv, defer_boxes=True)
+    ws = m.Workspace(B, cands.cap, 300, cuda_dev)
+    det = m.postprocess_dense(cands, ws, head, level_hw=lv, iou_thres=iou, max_det=300)
+    torch.cuda.synchronize()
+    images = [0, 17, 34, 63, 64, 81, 100, 127, 128, 150, 171, 191, 192, 213, 234, 255]
+    _oracle_vs_det(det, head_cpu, lv, conf, iou, images)

@@ -113,3 +113,22 @@ def test_half_output_matches_torch_half_semantics(cuda_dev):
         im /= 255                                                                               # torch's fp16 division on the device
         assert torch.equal(got, im), (H, W, imgsz)
         assert torch.equal(got.cpu(), olb.preprocess_ref(list(frames), (imgsz, imgsz)).half())
+
+
+def test_round2_golden_frames_test2_and_21_dataset_frames(cuda_dev, golden_dir):
+    """BASELINE configs[0]'s literal input (test2.png, read as yolo.py:360 reads it) plus ten dataset frames per
+    production size and the 1700x1034 one, both letterbox modes: the uint8 letterbox and the fp32 network input are
+    the bytes the real cv2 leaves produced in the dev container (tests/golden/make_golden_r2.py)."""
+    gold = json.load(open(os.path.join(golden_dir, "letterbox_golden_r2.json")))
+    assert len(gold) == 44
+    for key, g in sorted(gold.items()):
+        name, auto = key.split("|auto=")
+        im = cv2.imread(os.path.join(golden_dir, name))
+        assert list(im.shape[:2]) == g["src_hw"]
+        d = torch.from_numpy(im).to(cuda_dev)
+        got = m.letterbox(d, (640, 640), auto=bool(int(auto))).cpu().numpy()
+        assert list(got.shape) == g["shape"]
+        assert hashlib.sha256(got.tobytes()).hexdigest() == g["sha256"], key
+        net = m.preprocess(d, (640, 640), auto=bool(int(auto))).cpu().numpy()
+        assert list(net.shape) == g["net_shape"]
+        assert hashlib.sha256(net.tobytes()).hexdigest() == g["net_sha256"], key

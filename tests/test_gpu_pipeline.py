@@ -241,3 +241,68 @@ def test_plain_c_host_runs_the_path(cuda_dev, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
     assert "3 detections, 3 ROIs" in r.stdout
+
+
+def test_capacity_overflow_raises_on_every_host_path(cuda_dev):
+    """'raises rather than truncating silently'.  One image of a batch with more candidates than cap: the
+    fused kernel reports the unclamped count (and re-arms the counters itself: no memset between steps), and every host
+    entry that reads results back -- run_host, HostRunner, BatchStream.check_overflow, PipelineResult -- raises."""
+    B, nc, src_hw = 3, 64, (600, 960)
+    frames = synth.synth_frames(B, *src_hw, seed=2)
+    pipe = m.Pipeline(B, src_hw, nc, imgsz=640, conf=0.25, device=cuda_dev, cap=256, rois_per_frame=64)
+    head, _ = synth.synth_head_from_labels(B, nc, in_hw=pipe.in_hw, src_hw=src_hw, seed=2)
+    res = pipe(frames.to(cuda_dev), head.to(cuda_dev))
+    seen = res.cand_count.cpu().tolist()
+    assert max(seen) <= 256 and res.check_overflow() == max(seen)          # this batch fits
+    assert int(pipe.cands.count.abs().sum()) == 0                            # counters re-armed inside the kernel
+    res2 = pipe(frames.to(cuda_dev), head.to(cuda_dev))                      # second step without any memset: same counts
+    assert res2.cand_count.cpu().tolist() == seen
+    # image 1 gets 400 extra high-score anchors: more candidates than cap
+    hot = head.clone()
+    hot[1, 64 + 5, 100:500] = 4.0
+    res3 = pipe(frames.to(cuda_dev), hot.to(cuda_dev))
+    seen3 = res3.cand_count.cpu().tolist()
+    assert seen3[1] >= 400 > 256 and seen3[0] == seen[0] and seen3[2] == seen[2]
+    with pytest.raises(m.pipeline.CandidateOverflow):
+        res3.check_overflow()
+    with pytest.raises(m.pipeline.CandidateOverflow):
+        pipe.check_overflow()
+    with pytest.raises(m.pipeline.CandidateOverflow):
+        pipe.run_host(frames.pin_memory(), hot.pin_memory())
+    runner = m.HostRunner(pipe, depth=2, stage="full")
+    runner.submit(frames.pin_memory(), hot.pin_memory())
+    with pytest.raises(m.pipeline.CandidateOverflow):
+        runner.wait()
+    # the steps after the overflowing one are clean again (the kernel re-armed the counters)
+    runner2 = m.HostRunner(pipe, depth=2, stage="full")
+    rows, count, nroi = runner2.submit(frames.pin_memory(), head.pin_memory())
+    runner2.wait()
+    assert int(count.sum()) == int(res.det.count.sum())
+    # ROI capacity: fewer crop slots than rank-class detections -> RoiOverflow, count not clamped
+    small = m.Pipeline(B, src_hw, nc, imgsz=640, conf=0.25, device=cuda_dev, cap=1024, rois_per_frame=1)
+    r = small(frames.to(cuda_dev), head.to(cuda_dev))
+    assert int(r.roi_count) > small.roi_cap == 3 and r.n_rois() == 3
+    with pytest.raises(m.pipeline.RoiOverflow):
+        r.check_overflow()
+    bs = m.BatchStream([small])
+    bs.capture([(frames.to(cuda_dev), head.to(cuda_dev))])
+    bs.submit()
+    with pytest.raises(m.pipeline.RoiOverflow):
+        bs.check_overflow()
+
+
+def test_empty_inputs_scale_boxes_and_nms(cuda_dev):
+    """an empty CUDA tensor has a NULL data pointer -- scale_boxes on (0,4) and non_max_suppression on a
+    prediction without candidates must work (upstream construct_result calls scale_boxes on every frame)."""
+    empty = torch.zeros((0, 6), device=cuda_dev)
+    out = m.scale_boxes((640, 640), empty[:, :4], (1200, 1920))
+    assert out.shape == (0, 4)
+    assert m.scale_boxes((640, 640), torch.zeros((0, 4), device=cuda_dev), (1200, 1920)).shape == (0, 4)
+    pred = torch.zeros((2, 4 + 8, 8400), device=cuda_dev)                    # nothing above conf
+    dets = m.non_max_suppression(pred, 0.25, 0.45)
+    assert [tuple(d.shape) for d in dets] == [(0, 6), (0, 6)]
+    for d in dets:
+        assert m.scale_boxes((640, 640), d[:, :4], (1200, 1920)).shape == (0, 4)
+    # too many anchors for the 16-bit anchor field of the sort key: refused, not mis-sorted
+    with pytest.raises(ValueError):
+        m.filter_decoded(torch.zeros((1, 4 + 2, 70000), device=cuda_dev), 0.25)

@@ -138,9 +138,10 @@ def test_select_rois_order_and_count(cuda_dev):
     assert n == len(exp)
     assert list(zip(rbatch[:n].cpu().tolist(), rdet[:n].cpu().tolist())) == exp
     assert torch.equal(rb[:n].cpu(), torch.stack([rows[b, i, :4] for b, i in exp]))
-    # capacity clamp
-    _, _, _, rc2 = m.select_rois(det, classes, nc, roi_cap=5)
-    assert int(rc2.cpu()) == 5
+    # capacity: rows beyond roi_cap are dropped, the count is NOT clamped (the host can tell)
+    rb2, rbatch2, rdet2, rc2 = m.select_rois(det, classes, nc, roi_cap=5)
+    assert int(rc2.cpu()) == len(exp)
+    assert list(zip(rbatch2.cpu().tolist(), rdet2.cpu().tolist())) == exp[:5]
 
 
 def test_classifier_chain_batched(cuda_dev, golden_dir):
@@ -182,3 +183,52 @@ def test_classifier_chain_batched(cuda_dev, golden_dir):
     assert sum(o["top1"] == l for o, l in zip(out, labels)) == 63                      # the reference's known answer
     texts_ok = sum(o["text"] == names[l] for o, l in zip(out, labels))
     assert texts_ok >= 60 and all(o["text"] in handoff.VALID_CARD_RANKS or o["text"] == "" for o in out)
+
+
+def test_all_579_reference_crops_bit_exact_and_top1(cuda_dev, golden_dir):
+    """Config 4's chain check: every crop of rank_classifier/{train,valid} (579) through K5 gives the bytes the real
+    PIL/torchvision transform produced (sha256 recorded in the dev container AND the live oracle on this box), and the
+    classifier's top-1 on those K5 outputs equals the oracle's for all 579 (63/67 correct on valid: results.csv:21)."""
+    import hashlib
+    import cv2
+    from manual_yolo_b200 import classifier as pc
+    z = np.load(os.path.join(golden_dir, "rank_crops_all.npz"))
+    offs = z["offs"]
+    crops = [cv2.imdecode(z["jpeg"][offs[i]:offs[i + 1]], cv2.IMREAD_COLOR) for i in range(len(offs) - 1)]
+    assert len(crops) == 579
+    H, W = 1200, 1920
+    frames, boxes, bidx = [], [], []
+    canvas = np.random.default_rng(1).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    x = y = 4
+    rowh = 0
+    for c in crops:
+        h, w = c.shape[:2]
+        if x + w + 4 > W:
+            x, y, rowh = 4, y + rowh + 4, 0
+        if y + h + 4 > H:
+            frames.append(canvas)
+            canvas = np.random.default_rng(len(frames) + 1).integers(0, 256, (H, W, 3), dtype=np.uint8)
+            x, y, rowh = 4, 4, 0
+        canvas[y:y + h, x:x + w] = c
+        boxes.append([x + 0.4, y + 0.2, x + w + 0.7, y + h + 0.5])       # int() truncation on the device
+        bidx.append(len(frames))
+        x, rowh = x + w + 4, max(rowh, h)
+    frames.append(canvas)
+    fr = torch.from_numpy(np.stack(frames)).to(cuda_dev)
+    out, valid = m.crop_resize_rois(fr, torch.tensor(boxes, dtype=torch.float32, device=cuda_dev),
+                                    torch.tensor(bidx, dtype=torch.int32, device=cuda_dev), pad=0)
+    assert valid.cpu().tolist() == [1] * 579
+    out_c = out.cpu()
+    u8 = (out_c * 255).round().to(torch.uint8)
+    assert torch.equal(u8.float().div(255), out_c)
+    for i, c in enumerate(crops):
+        assert hashlib.sha256(u8[i].numpy().tobytes()).hexdigest() == str(z["roi_sha256"][i]), i
+        if i % 8 == 0:                                                    # live PIL oracle on this box as well
+            assert torch.equal(out_c[i], oroi.classify_preprocess_ref(c)), i
+    kz = np.load(os.path.join(golden_dir, "rank_classifier_kat.npz"))
+    clf = pc.rank_classifier_from_arrays({k[2:]: kz[k] for k in kz.files if k.startswith("w:")}, ocls.NAMES, device=cuda_dev)
+    top1, _ = clf.predict(out)
+    top1 = top1.cpu().numpy()
+    assert np.array_equal(top1, z["oracle_top1"])
+    v = z["split"] == 1
+    assert int((top1[v] == z["labels"][v]).sum()) == 63 and int(v.sum()) == 67

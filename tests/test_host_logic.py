@@ -254,3 +254,92 @@ def test_clean_detections_golden(golden_dir):
         assert got["class_id"].tolist() == case["class_id"] and str(got["class_id"].dtype) == case["class_id_dtype"]
         assert got["confidence"].tolist() == case["confidence"] and str(got["confidence"].dtype) == case["confidence_dtype"]
         assert (None if got["tracker_id"] is None else got["tracker_id"].tolist()) == case["tracker_id"]
+
+
+# ---- product-side rank classifier loader (detect.py:21 without Ultralytics) -------------------------------------------
+def _kat_npz(golden_dir):
+    import os
+    return np.load(os.path.join(golden_dir, "rank_classifier_kat.npz"))
+
+
+def test_product_classifier_from_arrays_matches_oracle(golden_dir):
+    from manual_yolo_b200 import classifier as pc
+    from oracle import classifier as oc
+    z = _kat_npz(golden_dir)
+    clf = pc.rank_classifier_from_arrays({k[2:]: z[k] for k in z.files if k.startswith("w:")}, oc.NAMES)
+    x = torch.from_numpy(z["roi_u8"]).float().div(255)
+    logits = clf.forward_logits(x)
+    assert torch.equal(logits, oc.forward_logits(oc.state_dict_from_npz(z), x))      # independent code, same torch ops
+    top1, conf = clf.predict(x)
+    assert int((top1.numpy() == z["labels"]).sum()) == 63                            # runs/rank_classifier/results.csv:21
+    assert float(conf.min()) > 0.0 and float(conf.max()) <= 1.0
+
+
+@pytest.mark.reference
+def test_product_classifier_loads_reference_checkpoint(golden_dir):
+    """rank_classifier.pt (detect.py:21) through the restricted unpickler: no Ultralytics, no oracle."""
+    import pickle
+    from manual_yolo_b200 import classifier as pc
+    clf = pc.load_rank_classifier("/root/reference/rank_classifier.pt")
+    assert clf.names == {0: "10", 1: "2", 2: "3", 3: "4", 4: "5", 5: "6", 6: "7", 7: "8", 8: "9", 9: "A", 10: "J", 11: "K", 12: "Q"}
+    assert clf.imgsz == 64 and clf.bn_eps == 1e-5
+    z = _kat_npz(golden_dir)
+    x = torch.from_numpy(z["roi_u8"]).float().div(255)
+    assert int((clf.predict(x)[0].numpy() == z["labels"]).sum()) == 63
+    # a pickle that references anything outside torch / containers / ultralytics shells is refused
+    import io
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("true",))
+    with pytest.raises(pickle.UnpicklingError):
+        pc._RestrictedUnpickler(io.BytesIO(pickle.dumps(Evil()))).load()
+
+
+def test_div255_two_constant_form_is_exact():
+    """K5's table-free v/255 (csrc/roi.cu top_byte_div255): RN(v*c_hi + RN(v*c_lo)) == RN(v/255) for every v in 0..255,
+    evaluated with exact rational arithmetic (one rounding per fp32 op, as FMUL / FFMA round)."""
+    from fractions import Fraction as Fr
+
+    def rn32(fr):
+        c = np.float32(float(fr))
+        best = None
+        for cand in (np.nextafter(c, np.float32(-np.inf)), c, np.nextafter(c, np.float32(np.inf))):
+            d = abs(Fr(float(cand)) - fr)
+            even = (int(np.float32(cand).view(np.uint32)) & 1) == 0
+            if best is None or d < best[0] or (d == best[0] and even):
+                best = (d, np.float32(cand))
+        return best[1]
+    c_hi = np.uint32(0x3B808081).view(np.float32)
+    c_lo = np.uint32(0xAF7F00BF).view(np.float32)
+    for v in range(256):
+        t = rn32(Fr(v) * Fr(float(c_lo)))
+        r = rn32(Fr(v) * Fr(float(c_hi)) + Fr(float(t)))
+        assert r == np.float32(v) / np.float32(255), v
+
+
+def test_round2_golden_fixtures_are_consistent(golden_dir):
+    """The committed round-2 fixtures: test2.png is the 1600x900 BGRA capture; 22 frames x 2 letterbox modes; 579 crops,
+    67 of them the validation split with 63 oracle hits (results.csv:21)."""
+    import json
+    import os
+    import cv2
+    gold = json.load(open(os.path.join(golden_dir, "letterbox_golden_r2.json")))
+    assert len(gold) == 44
+    assert cv2.imread(os.path.join(golden_dir, "frames", "test2.png"), cv2.IMREAD_UNCHANGED).shape == (900, 1600, 4)
+    assert gold["frames/test2.png|auto=1"]["shape"] == [384, 640, 3] and gold["frames/test2.png|auto=0"]["shape"] == [640, 640, 3]
+    sizes = sorted({tuple(v["src_hw"]) for v in gold.values()})
+    assert sizes == [(900, 1600), (1034, 1700), (1200, 1920)]
+    # the recorded hashes are what the real cv2 leaves give on this box too
+    import hashlib
+    from oracle import letterbox as olb2
+    for key in ("frames/test2.png|auto=0", "frames/test2.png|auto=1", "frames_r2/f1700x1034_00.jpg|auto=1"):
+        name, auto = key.split("|auto=")
+        im = cv2.imread(os.path.join(golden_dir, name))
+        lb = olb2.letterbox_ref(im, (640, 640), auto=bool(int(auto)))
+        assert hashlib.sha256(lb.tobytes()).hexdigest() == gold[key]["sha256"]
+    z = np.load(os.path.join(golden_dir, "rank_crops_all.npz"))
+    v = z["split"] == 1
+    assert len(z["labels"]) == 579 and int(v.sum()) == 67
+    assert int((z["oracle_top1"][v] == z["labels"][v]).sum()) == 63
