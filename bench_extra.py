@@ -90,6 +90,36 @@ def config3(dev, B=256, nc=80, cpu_images=4):
     m.nms_sorted(cands, ws, 0.7, max_det=300)
     out["dense_chain_equals_stagewise"] = bool(torch.equal(ws2.det.count, ws.det.count) and
                                                torch.equal(ws2.det.anchor[:, :1], ws.det.anchor[:, :1]))
+    # the same chain on sub-batches of the images, each on its own stream (api.DenseChain): the latency-bound
+    # per-image kernels (select-sort, NMS) of one sub-batch run underneath the HBM-bound ones of another
+    def graphed(fn):
+        """fn captured once into a CUDA graph (how a deployment drives the chain: one launch per batch)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+    g1 = graphed(chain)
+    r = timed(lambda: g1.replay(), flush=flush)
+    r["us_per_image"] = r["us_median"] / B
+    r["algo_GBps"] = head.numel() * 4 / (r["us_median"] * 1e-6) / 1e9
+    out["dense_chain_total_cuda_graph"] = r
+    del g1
+    for splits in (2, 3, 4):
+        dc = m.DenseChain(B, cands2.cap, 300, dev, splits=splits)
+        gd = graphed(lambda: dc(head, conf_thres=0.001, iou_thres=0.7, level_hw=lv))
+        r = timed(lambda: gd.replay(), flush=flush)
+        r["us_per_image"] = r["us_median"] / B
+        r["algo_GBps"] = head.numel() * 4 / (r["us_median"] * 1e-6) / 1e9
+        r["equals_single_stream"] = bool(torch.equal(dc.det.count, ws2.det.count) and torch.equal(dc.det.anchor, ws2.det.anchor)
+                                         and torch.equal(dc.det.rows, ws2.det.rows))
+        out[f"dense_chain_{splits}_streams_cuda_graph"] = r
+        del gd, dc
     if not cpu_images:
         return out
     # CPU oracle on a sub-sample, scaled (flagged)

@@ -382,14 +382,18 @@ class Detections:
 class Workspace:
     """Caller-owned scratch for sort/NMS (order array + oversize-image spill)."""
 
-    def __init__(self, B, cap, max_det, device):
+    def __init__(self, B, cap, max_det, device, det: Optional["Detections"] = None):
+        """``det``: write the detections into these (B, max_det, ..) buffers (e.g. slices of a larger batch)."""
         self.B, self.cap, self.max_det = B, cap, max_det
         self.order = torch.empty((B, cap), dtype=torch.int32, device=device)
         nbytes = int(_lib.load().b200yolo_workspace_bytes(B, cap))
         self.ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=device)
-        self.det = Detections(torch.empty((B, max_det, 6), dtype=torch.float32, device=device),
-                              torch.empty((B, max_det), dtype=torch.int32, device=device),
-                              torch.empty((B,), dtype=torch.int32, device=device))
+        if det is not None and (tuple(det.rows.shape) != (B, max_det, 6) or not det.rows.is_contiguous()):
+            raise ValueError("det buffers do not match (B, max_det)")
+        self.det = det if det is not None else Detections(
+            torch.empty((B, max_det, 6), dtype=torch.float32, device=device),
+            torch.empty((B, max_det), dtype=torch.int32, device=device),
+            torch.empty((B,), dtype=torch.int32, device=device))
 
 
 def sort_candidates(cands: Candidates, max_nms=30000, ws: Optional[Workspace] = None) -> Workspace:
@@ -441,6 +445,53 @@ def postprocess_dense(cands: Candidates, ws: Workspace, head, strides=(8, 16, 32
     _lib.check(rc, "postprocess_dense")
     del keep
     return ws.det
+
+
+class DenseChain:
+    """The whole low-confidence (evaluation-regime) chain -- class filter -> select-sort -> box decode -> windowed NMS
+    (``decode_and_filter(defer_boxes=True)`` + ``postprocess_dense``) -- on ``splits`` sub-batches of the images, each on
+    its own stream.  Images are independent, and the chain alternates HBM-bound kernels (class filter, box decode) with
+    latency-bound per-image ones (select-sort, NMS): with two or more sub-batches in flight the latency-bound kernels
+    of one run underneath the streaming kernels of another.  Results are those of the single-stream chain, bit for bit.
+    Fork/join with events on the caller's current stream: capturable into a CUDA graph."""
+
+    def __init__(self, B, cap, max_det, device, splits=2):
+        splits = max(1, min(int(splits), B))
+        self.B, self.cap, self.max_det, self.device = B, cap, max_det, torch.device(device)
+        self.det = Detections(torch.empty((B, max_det, 6), dtype=torch.float32, device=device),
+                              torch.empty((B, max_det), dtype=torch.int32, device=device),
+                              torch.zeros((B,), dtype=torch.int32, device=device))
+        self.cand_count = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.parts = []
+        for s in range(splits):
+            lo, hi = (s * B) // splits, ((s + 1) * B) // splits
+            n = hi - lo
+            cands = Candidates(torch.empty((n, cap, 6), dtype=torch.float32, device=device),
+                               torch.empty((n, cap), dtype=torch.int32, device=device), self.cand_count[lo:hi], cap)
+            ws = Workspace(n, cap, max_det, device, det=Detections(self.det.rows[lo:hi], self.det.anchor[lo:hi],
+                                                                    self.det.count[lo:hi]))
+            self.parts.append((lo, hi, cands, ws))
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.parts] if splits > 1 else [None]
+
+    def __call__(self, head, strides=(8, 16, 32), conf_thres=0.001, iou_thres=0.7, classes=None, in_hw=None, level_hw=None,
+                 agnostic=False, max_nms=30000, max_wh=7680, scale: Optional[torch.Tensor] = None,
+                 roi_mask: Optional[torch.Tensor] = None, roi_nc=0, roi_cnt: Optional[torch.Tensor] = None) -> "Detections":
+        cur = torch.cuda.current_stream()
+        for (lo, hi, cands, ws), st in zip(self.parts, self.streams):
+            h = [x[lo:hi] for x in head] if isinstance(head, (list, tuple)) else head[lo:hi]
+            if st is not None:
+                st.wait_stream(cur)                                       # fork
+            with torch.cuda.stream(st if st is not None else cur):
+                decode_and_filter(h, strides, conf_thres, classes, in_hw=in_hw, level_hw=level_hw, cap=self.cap, out=cands,
+                                  defer_boxes=True)
+                postprocess_dense(cands, ws, h, strides, in_hw=in_hw, level_hw=level_hw, iou_thres=iou_thres,
+                                  agnostic=agnostic, max_det=self.max_det, max_nms=max_nms, max_wh=max_wh,
+                                  scale=None if scale is None else scale[lo:hi], roi_mask=roi_mask, roi_nc=roi_nc,
+                                  roi_cnt=None if roi_cnt is None else roi_cnt[lo:hi])
+        for st in self.streams:
+            if st is not None:
+                cur.wait_stream(st)                                       # join
+        return self.det
 
 
 def nms_candidates(cands: Candidates, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680,

@@ -368,9 +368,10 @@ __global__ void __launch_bounds__(256, 6) box_decode_kernel(const Levels L, floa
   }
 }
 
-// Dense-regime form of the box decode (b200yolo_postprocess_dense): only the candidates the sort put in order
-// (the best 2048 of an image) are decoded -- the NMS consumes nothing else.  They are picked by the selection
-// threshold the sort published in the workspace header and visited in SLOT order (= runs of consecutive anchors,
+// Dense-regime form of the box decode (b200yolo_postprocess_dense): only the best kPre = 512 candidates of an image
+// (one NMS window: what greedy NMS with max_det = 300 typically consumes; anything beyond is decoded by the NMS
+// kernel itself, window by window) are decoded here.  They are picked by the threshold the sort published in the
+// workspace header and visited in SLOT order (= runs of consecutive anchors,
 // as the class filter compacted them), so every 32-byte sector of the DFL channels is fetched once, by one warp
 // group; walking order[] instead would touch one sector per 4 useful bytes.  A CTA takes 256 slots, compacts the
 // selected ones in shared memory and decodes them 64 at a time (4 lanes per box).  pass 1 is the fallback for
@@ -389,8 +390,9 @@ __global__ void __launch_bounds__(256, 6) box_decode_selected_kernel(const Level
     if (pass == 1 && !hdr[B + b]) continue;
     const int n = min(cand_count[b], cap);
     if (blk * 256 >= n) continue;
+    // the entries decoded ahead of the NMS: the best hdr[4B + b] of the image (threshold published by the sort)
     const unsigned long long thr48 = pass == 1 ? ~0ull
-        : (((unsigned long long)(uint32_t)hdr[3 * B + b] << 32) | (unsigned long long)(uint32_t)hdr[2 * B + b]);
+        : (((unsigned long long)(uint32_t)hdr[6 * B + b] << 32) | (unsigned long long)(uint32_t)hdr[5 * B + b]);
     const int s = blk * 256 + tid;
     bool pick = false;
     if (s < n) {

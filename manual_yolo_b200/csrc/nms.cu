@@ -22,10 +22,12 @@
 // are applied to every later box of the window in parallel.  ~19 KB of shared memory per CTA: several images per
 // SM, so a batch of 256 images is one wave.  Compiled with -fmad=false.
 
+#include "levels.cuh"
 #include "nms_common.cuh"
 
 namespace {
 
+using b200::Levels;
 using b200::box_meta;
 using b200::iou_suppresses;
 using b200::may_overlap;
@@ -42,7 +44,11 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
                                                  float* __restrict__ out, int* __restrict__ out_anchor,
                                                  int* __restrict__ out_count, const uint32_t* __restrict__ roi_mask,
                                                  int roi_nc, int* __restrict__ roi_cnt, int* __restrict__ hdr, int B,
-                                                 int pass) {
+                                                 int pass, const Levels L, int decode, float* __restrict__ cand_rw) {
+  // decode != 0 (b200yolo_postprocess_dense): the candidate rows hold score and class; the boxes of the first
+  // hdr[4B + b] sorted entries were decoded ahead of this kernel (in slot order: DRAM-friendly), the boxes of any
+  // later entry are DFL-decoded HERE, when its window is loaded -- so exactly the prefix of the sorted list the greedy
+  // NMS consumes is ever read from the head tensor (~500 of 8400 candidates per image in the conf = 0.001 regime).
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float4* box = reinterpret_cast<float4*>(smem_raw);                  // [kWindow] class-offset boxes of the window
   float4* kbox = box + kWindow;                                       // [max_det] kept boxes (all windows)
@@ -75,12 +81,47 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
   for (int w0 = 0; w0 < n; w0 += kWindow) {
     const int wn = min(kWindow, n - w0);
     const int kprev = kcount_s;               // keeps collected in earlier windows (uniform: read after a barrier)
-    // ---- load the window; test it against the kept boxes of earlier windows ----
+    // ---- load the window (decode mode: DFL-decode the boxes that were not decoded ahead, 4 lanes per box) ----
+    const int n_pre = decode ? (pass == 0 ? hdr[4 * B + b] : 0) : n;     // sorted entries whose rows hold boxes already
+    const bool dec_win = decode && w0 + wn > n_pre;
+    if (dec_win) {
+      const int r_lo = max(0, n_pre - w0);
+      for (int q = tid; q < (((wn - r_lo) * 4 + 31) & ~31); q += NT) {   // whole warps: the quad shuffles need every lane
+        const int r = r_lo + (q >> 2), sd = q & 3;
+        const bool act = r < wn;
+        const int slot = act ? orow[w0 + r] : 0;
+        const b200::AnchorRef ar = b200::anchor_ref(L, b, act ? cand_anchor[(int64_t)b * cap + slot] : 0);
+        const float d = act ? b200::dfl_side(ar.p + (long long)(sd * b200::kReg) * ar.cs, ar.cs) : 0.f;
+        const int q0 = lane & ~3;
+        const float d0 = __shfl_sync(0xffffffffu, d, q0), d1 = __shfl_sync(0xffffffffu, d, q0 + 1);
+        const float d2 = __shfl_sync(0xffffffffu, d, q0 + 2), d3 = __shfl_sync(0xffffffffu, d, q0 + 3);
+        if (act && sd == 0) {
+          const float4 bx = b200::decode_box(ar, d0, d1, d2, d3);
+          float2* g = reinterpret_cast<float2*>(cand_rw + ((int64_t)b * cap + slot) * 6);   // keep the global rows complete
+          g[0] = make_float2(bx.x, bx.y);
+          g[1] = make_float2(bx.z, bx.w);
+          const float cls = crow[(int64_t)slot * 6 + 5];
+          const float rowv[6] = {bx.x, bx.y, bx.z, bx.w, 0.f, cls};
+          const float c = agnostic ? 0.f : __fmul_rn(cls, max_wh);
+          box[r] = make_float4(__fadd_rn(bx.x, c), __fadd_rn(bx.y, c), __fadd_rn(bx.z, c), __fadd_rn(bx.w, c));
+          meta[r] = box_meta(rowv, max_wh, agnostic);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- test the window against the kept boxes of earlier windows ----
     for (int r = tid; r < wn; r += NT) {
-      const float* row = crow + (int64_t)orow[w0 + r] * 6;
-      const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
-      const float4 bj = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
-      const int mj = box_meta(row, max_wh, agnostic);
+      float4 bj;
+      int mj;
+      const bool have = dec_win && w0 + r >= n_pre;          // decoded above, already in shared memory
+      if (have) {
+        bj = box[r]; mj = meta[r];
+      } else {
+        const float* row = crow + (int64_t)orow[w0 + r] * 6;
+        const float c = agnostic ? 0.f : __fmul_rn(row[5], max_wh);
+        bj = make_float4(__fadd_rn(row[0], c), __fadd_rn(row[1], c), __fadd_rn(row[2], c), __fadd_rn(row[3], c));
+        mj = box_meta(row, max_wh, agnostic);
+      }
       bool dead = false;
       for (int k = 0; k < kprev && !dead; ++k) {
         if (!may_overlap(kmeta[k], mj)) continue;
@@ -88,7 +129,8 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
         const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
         dead = iou_suppresses(bi, ai, bj, thr);
       }
-      box[r] = bj; meta[r] = mj; rem[r] = dead ? 1 : 0;
+      if (!have) { box[r] = bj; meta[r] = mj; }
+      rem[r] = dead ? 1 : 0;
     }
     __syncthreads();
 
@@ -124,21 +166,41 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
         if (lane == 0) rem_bits[wid] = bits;
       }
       __syncthreads();
-      // ---- (B) serial resolve of the chunk ----
-      if (tid == 0) {
-        const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-        unsigned long long alive = valid & ~(((unsigned long long)rem_bits[1] << 32) | rem_bits[0]);
-        unsigned long long kept = 0;
-        int kc = kcount_s;
-        while (alive && kc < max_det) {                     // the only serial part: bit operations on the mask rows
-          const int i = __ffsll((long long)alive) - 1;
-          kept |= 1ull << i;
-          ++kc;
-          alive &= ~mask[i];
-          alive &= ~(1ull << i);
+      // ---- (B) serial resolve of the chunk.  Only boxes whose mask row is non-zero can suppress anything: runs of
+      //      alive boxes with empty rows are kept in one step, so the loop iterates once per SUPPRESSING box ----
+      if (tid < 32) {
+        const unsigned long long r0 = mask[lane], r1 = mask[lane + 32];
+        const unsigned nz0 = __ballot_sync(0xffffffffu, lane < m && r0 != 0ull);
+        const unsigned nz1 = __ballot_sync(0xffffffffu, lane + 32 < m && r1 != 0ull);
+        if (lane == 0) {
+          const unsigned long long nz = ((unsigned long long)nz1 << 32) | nz0;
+          const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+          unsigned long long alive = valid & ~(((unsigned long long)rem_bits[1] << 32) | rem_bits[0]);
+          unsigned long long kept = 0;
+          int kc = kcount_s;
+          while (alive && kc < max_det) {
+            const unsigned long long hot = alive & nz;              // alive boxes that may suppress later ones
+            const int stop = hot ? __ffsll((long long)hot) - 1 : 64;
+            const unsigned long long run = stop ? alive & (stop == 64 ? ~0ull : ((1ull << stop) - 1ull)) : 0ull;
+            if (run) {                                              // harmless boxes before the next suppressor
+              const int c = __popcll(run);
+              if (kc + c <= max_det) { kept |= run; kc += c; alive &= ~run; }
+              else {                                                // max_det falls inside the run: bit by bit
+                unsigned long long rr = run;
+                while (rr && kc < max_det) { const int i = __ffsll((long long)rr) - 1; kept |= 1ull << i; ++kc; rr &= rr - 1; }
+                alive = 0;
+              }
+              continue;
+            }
+            const int i = stop;                                     // the next alive suppressor
+            kept |= 1ull << i;
+            ++kc;
+            alive &= ~mask[i];
+            alive &= ~(1ull << i);
+          }
+          kept_bits_s = kept;
+          kcount_s = kc;
         }
-        kept_bits_s = kept;
-        kcount_s = kc;
       }
       __syncthreads();
       {   // record the chunk's keeps in parallel: rank inside the chunk = number of kept boxes before it
@@ -244,7 +306,17 @@ static int nms_check(const NmsArgs& a) {
   return B200YOLO_OK;
 }
 
-static int nms_launch(const NmsArgs& a, int* hdr, int pass, cudaStream_t s) {
+static int nms_launch(const NmsArgs& a, int* hdr, int pass, cudaStream_t s, const Levels* levels = nullptr) {
+  Levels L;
+  if (levels) L = *levels;
+  else {
+    for (int l = 0; l < B200YOLO_MAX_LEVELS; ++l) {
+      L.ptr[l] = nullptr; L.bstride[l] = 0; L.cstride[l] = 0; L.w[l] = 1; L.stride[l] = 1.f; L.off[l] = 0;
+    }
+    L.off[B200YOLO_MAX_LEVELS] = 0; L.n = 1;
+  }
+  const int decode = levels ? 1 : 0;
+  float* cand_rw = const_cast<float*>(a.cand);
   const size_t md4 = ((size_t)a.max_det + 3) & ~(size_t)3;
   const size_t smem = (size_t)kWindow * 16 + md4 * 16 + (size_t)kWindow * 4 + md4 * 4 + md4 * 4 + (size_t)kWindow;
   if (a.cap <= 1024) {
@@ -256,7 +328,7 @@ static int nms_launch(const NmsArgs& a, int* hdr, int pass, cudaStream_t s) {
     }
     kern<<<a.B, NT, smem, s>>>(a.cand, a.cand_anchor, a.cand_count, a.order, a.cap, a.max_nms, a.iou_thres, a.max_wh,
                                a.agnostic, a.max_det, a.scale, a.out, a.out_anchor, a.out_count, a.roi_class_mask,
-                               a.roi_nc, a.roi_cnt, hdr, a.B, pass);
+                               a.roi_nc, a.roi_cnt, hdr, a.B, pass, L, decode, cand_rw);
   } else {
     constexpr int NT = 512;
     auto kern = nms_kernel<NT>;
@@ -266,7 +338,7 @@ static int nms_launch(const NmsArgs& a, int* hdr, int pass, cudaStream_t s) {
     }
     kern<<<a.B, NT, smem, s>>>(a.cand, a.cand_anchor, a.cand_count, a.order, a.cap, a.max_nms, a.iou_thres, a.max_wh,
                                a.agnostic, a.max_det, a.scale, a.out, a.out_anchor, a.out_count, a.roi_class_mask,
-                               a.roi_nc, a.roi_cnt, hdr, a.B, pass);
+                               a.roi_nc, a.roi_cnt, hdr, a.B, pass, L, decode, cand_rw);
   }
   return b200_launch_status();
 }
@@ -298,8 +370,9 @@ extern "C" int b200yolo_nms(const float* cand, const int* cand_anchor, const int
 // K2b + K3 + K4 for the dense regime (cap > 1024, e.g. conf = 0.001 evaluation: every anchor is a candidate).
 // The candidates come from b200yolo_class_filter (scores and classes only).  Sorting needs no boxes, and greedy NMS
 // stops at max_det keeps, so the work is ordered to touch only what the NMS consumes: select + sort the best 2048
-// entries per image, DFL-decode exactly those, NMS over them.  An image whose NMS runs out of ordered entries is
-// flagged and re-done with the full sort and the full decode (same stream, launches exit at once otherwise).
+// entries per image, then the NMS kernel DFL-decodes each window of 512 sorted candidates as it loads it -- about
+// 500 boxes per image in the conf = 0.001 regime instead of all 8400 (or the 2048 ordered ones).  An image whose NMS
+// runs out of ordered entries is flagged and re-done after the full sort (same stream, launches exit at once otherwise).
 extern "C" int b200yolo_postprocess_dense(const b200yolo_level* levels, int n_levels, float* cand,
                                           const int* cand_anchor, const int* cand_count, int B, int cap, int max_nms,
                                           double iou_thres, float max_wh, int agnostic, int max_det,
@@ -315,12 +388,17 @@ extern "C" int b200yolo_postprocess_dense(const b200yolo_level* levels, int n_le
   B200_REQUIRE(workspace_bytes >= b200yolo_workspace_bytes(B, cap), B200YOLO_ERR_WORKSPACE);
   int* hdr = reinterpret_cast<int*>(workspace);
   cudaStream_t s = (cudaStream_t)stream;
+  Levels L;
+  rc = b200::build_levels(levels, n_levels, L);
+  if (rc != B200YOLO_OK) return rc;
   for (int pass = 0; pass < (cap > 2048 ? 2 : 1); ++pass) {
     rc = b200_sort_launch(cand, cand_anchor, cand_count, B, cap, max_nms, order, workspace, workspace_bytes, pass, s);
     if (rc != B200YOLO_OK) return rc;
-    rc = b200_box_decode_sorted_launch(levels, n_levels, cand, cand_anchor, cand_count, order, B, cap, max_nms, hdr, pass, s);
-    if (rc != B200YOLO_OK) return rc;
-    rc = nms_launch(a, hdr, pass, s);
+    if (pass == 0) {   // boxes of the best 512 entries per image, in slot order
+      rc = b200_box_decode_sorted_launch(levels, n_levels, cand, cand_anchor, cand_count, order, B, cap, max_nms, hdr, 0, s);
+      if (rc != B200YOLO_OK) return rc;
+    }
+    rc = nms_launch(a, hdr, pass, s, &L);       // decodes the boxes of any further window it consumes
     if (rc != B200YOLO_OK) return rc;
   }
   return B200YOLO_OK;

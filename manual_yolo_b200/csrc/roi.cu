@@ -294,11 +294,7 @@ struct FastSmem {
 // 2^23 + v by one byte permute, v/255 = RN(v * c_hi + RN(v * c_lo)) with c_hi + c_lo = 1/255 to 48 bits -- equal to
 // IEEE v / 255.0f for every v in [0, 255] (checked exhaustively on the host in tests/test_host_logic.py and, through
 // every K5 output, against PIL on the device).
-__device__ __forceinline__ float top_byte_div255(uint32_t a) {
-  const float v = __fsub_rn(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7443)), 8388608.0f);
-  return __fmaf_rn(v, __uint_as_float(0x3B808081u), __fmul_rn(v, __uint_as_float(0xAF7F00BFu)));
-}
-// The same for two accumulators at once with Blackwell's packed fp32 pipe (SASS FADD2 / FMUL2 / FFMA2).
+// Two accumulators at a time on Blackwell's packed fp32 pipe (SASS FADD2 / FMUL2 / FFMA2).
 __device__ __forceinline__ float2 top_byte_div255_x2(uint32_t a, uint32_t b) {
   float2 d;
   asm("{\n\t"

@@ -48,8 +48,11 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
   if (pass == 1 && !(hdr && hdr[B + b])) return;           // fallback launch: only the images the NMS flagged
   const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
   const int n_out = min(max(n, 0), max_nms);
-  if (hdr && tid == 0) {   // every entry sorted, no fallback pending, threshold = "every key"
+  if (hdr && tid == 0) {   // every entry sorted, no fallback pending, thresholds = "every key"
     hdr[b] = n_out; hdr[2 * B + b] = -1; hdr[3 * B + b] = -1;
+    // boxes decoded ahead of the NMS: pass 0 -> all of them (the decode kernel takes every key); pass 1 (fallback
+    // re-sort): none is assumed -- the NMS decodes every window it loads
+    hdr[4 * B + b] = pass == 0 ? n_out : 0; hdr[5 * B + b] = -1; hdr[6 * B + b] = -1;
     if (pass == 0) hdr[B + b] = 0;
   }
   if (n <= 0) return;
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
 
 // ---- dense regime: select the best kSelK keys, sort only those ----------------------------------------
 constexpr int kSelK = 2048;
+constexpr int kPre = 512;          // entries whose boxes b200yolo_postprocess_dense decodes ahead of the NMS (one NMS window)
 
 __device__ __forceinline__ void bitonic_sort_2048(uint64_t* s, int tid, int nt) {
   for (int k = 2; k <= kSelK; k <<= 1) {
@@ -188,7 +192,10 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
   const int n_out = min(max(n, 0), max_nms);
-  if (tid == 0) { hdr[b] = min(n_out, kSelK); hdr[B + b] = 0; hdr[2 * B + b] = -1; hdr[3 * B + b] = -1; }
+  if (tid == 0) {
+    hdr[b] = min(n_out, kSelK); hdr[B + b] = 0; hdr[2 * B + b] = -1; hdr[3 * B + b] = -1;
+    hdr[4 * B + b] = min(n_out, kPre); hdr[5 * B + b] = -1; hdr[6 * B + b] = -1;     // (all ones: every key) for n <= kPre
+  }
   if (n <= 0) return;
   if (!keys_in_smem) src = ws + (int64_t)b * 2 * cap;
   const float* crow = cand + (int64_t)b * cap * 6;
@@ -270,14 +277,20 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
   bitonic_sort_2048(sB, tid, NT);
   const int m = min(n_out, kSelK);
   for (int r = tid; r < m; r += NT) orow[r] = (int)(sB[r] & 0xffff);
+  if (tid == 0 && n > kPre) {
+    // threshold of the kPre best entries: the box decode ahead of the NMS takes exactly those (in slot order)
+    const unsigned long long t = sB[min(m, kPre) - 1] >> 16;
+    hdr[5 * B + b] = (int)(uint32_t)(t & 0xffffffffu); hdr[6 * B + b] = (int)(uint32_t)(t >> 32);
+  }
 }
 
 }  // namespace
 
-// Workspace layout: [header: 4 x B ints -- entries of order[] that are sorted | image needs the full-sort fallback |
-// low 32 / high 16 bits of the selection threshold (key >> 16 of the last ordered entry; all ones = every key) --
-// padded to 16 B][payload: per image 2 * cap u64 keys, used when cap exceeds the shared-memory paths].
-static size_t ws_header_bytes(int B) { return (((size_t)B * 4 * sizeof(int)) + 15) & ~(size_t)15; }
+// Workspace layout: [header: 7 x B ints -- entries of order[] that are sorted | image needs the full-sort fallback |
+// low 32 / high 16 bits of the selection threshold (key >> 16 of the last ordered entry; all ones = every key) |
+// entries whose boxes are decoded ahead of the NMS | low / high bits of their threshold -- padded to 16 B]
+// [payload: per image 2 * cap u64 keys, used when cap exceeds the shared-memory paths].
+static size_t ws_header_bytes(int B) { return (((size_t)B * 7 * sizeof(int)) + 15) & ~(size_t)15; }
 
 extern "C" size_t b200yolo_workspace_bytes(int B, int cap) {
   if (B <= 0 || cap <= 0) return 0;

@@ -51,7 +51,7 @@ def test_argument_errors_before_any_launch():
     assert lib.b200yolo_roi_crop_resize(one, 1, 8, 8, 24, 192, one, one, null, 4, 6, 128, one, one, null) == -4
     assert lib.b200yolo_postprocess_small(None, 0, one, one, one, 1, 2048, 30000, 0.5, 7680.0, 0, 300, null, one, one, one,
                                           null, 0, null, null, null) == -4
-    hdr = 64                                                     # 4 ints per image (sorted count, fallback flag, threshold), 16-B padded
+    hdr = 112                                                    # 7 ints per image (sorted count, fallback flag, 2 thresholds, decoded count), 16-B padded
     assert lib.b200yolo_workspace_bytes(4, 8400) == hdr + 16
     assert lib.b200yolo_workspace_bytes(4, 20000) == hdr + 4 * (20000 + 1250) * 16
     with pytest.raises(ValueError):
