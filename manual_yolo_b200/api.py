@@ -595,6 +595,37 @@ def crop_resize_rois(frames, boxes_xyxy, batch_idx, pad=6, size=64, roi_count=No
     return out, valid
 
 
+def classify_preprocess(crops, size=64, device="cuda"):
+    """``ClassificationPredictor.preprocess`` drop-in for a list of host crops (``rank_model(crop)``,
+    ``/root/reference/detect.py:121``: BGR HWC uint8 numpy arrays of any sizes): the crops are stacked into one pinned
+    canvas, uploaded once, and resized by K5 in one launch (``pad=0``: every box is exactly its crop) -- BGR->RGB,
+    Pillow-exact ``Resize(64)`` + ``CenterCrop(64)`` + ``ToTensor``.  Returns (N,3,size,size) fp32 on ``device``."""
+    import numpy as np
+    if not crops:
+        return torch.empty((0, 3, size, size), dtype=torch.float32, device=device)
+    for c in crops:
+        if not isinstance(c, np.ndarray) or c.ndim != 3 or c.shape[2] != 3 or c.dtype != np.uint8 or c.size == 0:
+            raise ValueError("crops must be non-empty HxWx3 uint8 numpy arrays (BGR)")
+    wmax = max(c.shape[1] for c in crops)
+    W = ((wmax + 8) * 3 + 15) // 16 * 16 // 3 + 16           # a few spare columns: no crop touches the buffer's edge
+    H = sum(c.shape[0] for c in crops) + 2                    # one spare row above and below
+    canvas = torch.zeros((1, H, W, 3), dtype=torch.uint8).pin_memory()
+    cv = canvas.numpy()
+    boxes, y = [], 1
+    for c in crops:
+        h, w = c.shape[:2]
+        cv[0, y:y + h, 4:4 + w] = c
+        boxes.append([4.0, float(y), float(4 + w), float(y + h)])
+        y += h
+    d = canvas.to(device, non_blocking=True)
+    bx = torch.tensor(boxes, dtype=torch.float32).to(device, non_blocking=True)
+    bidx = torch.zeros((len(crops),), dtype=torch.int32, device=device)
+    out, valid = crop_resize_rois(d, bx, bidx, pad=0, size=size)
+    if int((valid <= 0).sum()):
+        raise ValueError("a crop is outside the K5 envelope (short side > 31 x 64 px)")
+    return out
+
+
 def rois_from_detections(frames, det: Detections, roi_cnt, roi_mask, nc, roi_cap, pad=6, size=64, out=None):
     """Pipeline form of K5: crops + resizes every detection whose class is in ``roi_mask`` straight from
     the NMS output (``roi_cnt`` = per-image counts written by ``nms_sorted``).  Returns
