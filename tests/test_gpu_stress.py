@@ -79,3 +79,14 @@ def test_nms_random_sizes_and_overlaps(cuda_dev):
         out, idx = m.non_max_suppression(pred.to(cuda_dev), 0.05, iou, agnostic=agn, max_det=max_det, return_idxs=True)
         for b in range(2):
             assert torch.equal(idx[b].cpu(), ref_idx[b]) and torch.equal(out[b].cpu(), ref_out[b]), (A, nc, ncl, iou, max_det, agn)
+
+
+def test_sanitize_cases_run_clean(cuda_dev):
+    """tools/sanitize_cases.py (the small-shape driver for compute-sanitizer, which this pool refuses to run) must at
+    least run clean on its own: every kernel with hand-rolled synchronisation, on its edge shapes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_cases.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sanitize cases ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
