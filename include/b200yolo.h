@@ -222,13 +222,26 @@ int b200yolo_select_rois(const float* det, const int* det_count, int B, int max_
                          const uint32_t* class_mask, int nc, float* roi_boxes, int* roi_batch,
                          int* roi_det, int* roi_count, int roi_cap, void* stream);
 
-/* Merge step of sliced prediction: det (n_frames * n_slices, max_det, 6) / det_count from b200yolo_nms hold each
+/* Merge input of sliced prediction: det (n_frames * n_slices, max_det, 6) / det_count from b200yolo_nms hold each
  * slice's kept detections in slice pixels; per frame they are concatenated (slice-major, rank order), shifted by
  * the slice origin (SAHI shift_amount) and written as candidates (cand (n_frames, cap, 6), cand_anchor =
- * slice * max_det + rank, cand_count not clamped) for one more b200yolo_sort_topk + b200yolo_nms over the frame. */
+ * slice * max_det + rank, cand_count not clamped).  full_det / full_count: optional (n_frames, max_det, 6) / (n_frames)
+ * detections of the FULL frame in frame pixels -- SAHI's perform_standard_pred=True, its default -- appended after the
+ * slices (cand_anchor = n_slices * max_det + rank).  The candidates feed b200yolo_greedy_nmm (SAHI's default merge)
+ * or one more b200yolo_sort_topk + b200yolo_nms. */
 int b200yolo_gather_slice_detections(const float* det, const int* det_count, int n_frames, int n_slices,
-                                     int max_det, const int* slice_xy, float* cand, int* cand_anchor,
-                                     int* cand_count, int cap, void* stream);
+                                     int max_det, const int* slice_xy, const float* full_det, const int* full_count,
+                                     float* cand, int* cand_anchor, int* cand_count, int cap, void* stream);
+
+/* SAHI's default merge of the gathered predictions (sahi.predict.get_sliced_prediction as called at pipe.py:186-193:
+ * postprocess_type "GREEDYNMM", match_metric "IOS" = 1 ("IOU" = 0), match_threshold 0.5, class-aware): greedy
+ * non-maximum MERGING -- a matched box is merged into the kept one (union box, max score) instead of being dropped.
+ * cand / cand_src / cand_count: as written by b200yolo_gather_slice_detections (cap <= 8192).  out: (n_frames,
+ * max_det, 6) merged rows in descending score of the kept boxes; out_src: (n_frames, max_det) provenance of each kept
+ * box; out_count: (n_frames).  roi_class_mask / roi_nc / roi_cnt: as for b200yolo_nms. */
+int b200yolo_greedy_nmm(const float* cand, const int* cand_src, const int* cand_count, int n_frames, int cap,
+                        int match_metric, double match_threshold, int agnostic, int max_det, float* out, int* out_src,
+                        int* out_count, const uint32_t* roi_class_mask, int roi_nc, int* roi_cnt, void* stream);
 
 /* ---- N2: tracker association costs -------------------------------------------------------------------------
  * The reference hands each frame's detections to supervision ByteTrack (detect.py:557); its association step is

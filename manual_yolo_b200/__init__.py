@@ -7,7 +7,7 @@ hand-written CUDA behind the C ABI of ``include/b200yolo.h`` (``libb200yolo.so``
 from . import classifier, geometry, handoff  # noqa: F401
 from .classifier import RankClassifier, load_rank_classifier  # noqa: F401
 from .api import (Candidates, DenseChain, Detections, Workspace, classify_preprocess, crop_resize_rois, decode_and_filter, filter_decoded,  # noqa: F401
-                  gather_slice_detections, iou_cost_matrix, preprocess_slices,
+                  gather_slice_detections, greedy_nmm, iou_cost_matrix, preprocess_slices,
                   letterbox, nms_candidates, nms_sorted, non_max_suppression, postprocess_dense, postprocess_small,
                   preprocess,
                   rois_from_detections, scale_boxes, scale_params_tensor,

@@ -62,8 +62,10 @@ SIGNATURES = {
     "b200yolo_letterbox_slices_u8_to_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, POINTER(c_int), c_int,
                                                     c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                                     c_int, c_int, c_void_p]),
-    "b200yolo_gather_slice_detections": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), c_void_p,
-                                                 c_void_p, c_void_p, c_int, c_void_p]),
+    "b200yolo_gather_slice_detections": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "b200yolo_greedy_nmm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200yolo_iou_cost_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                          c_void_p, c_void_p]),
     "b200yolo_selftest_math": (c_int, [c_int, ctypes.c_uint64, c_void_p, c_void_p]),

