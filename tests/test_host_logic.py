@@ -365,4 +365,5 @@ def test_oracle_greedy_nmm_semantics():
     # a chain: B overlaps A, C overlaps the union of A and B more than A alone -> merged box grows as it merges
     q = torch.tensor([[0., 0., 50., 50., 0.9, 0.], [20., 0., 80., 50., 0.8, 0.], [45., 0., 70., 50., 0.7, 0.]])
     out, _ = slicing.greedy_nmm_postprocess_ref(q, "IOS", 0.5, class_agnostic=True)
-    assert sorted(out.tolist()) == [[0., 0., 80., 50., 0.9, 0.], [45., 0., 70., 50., 0.7, 0.]]   # C only overlaps the grown box
+    exp2 = torch.tensor([[0., 0., 80., 50., 0.9, 0.], [45., 0., 70., 50., 0.7, 0.]])            # C only overlaps the grown box
+    assert torch.equal(torch.tensor(sorted(out.tolist())), exp2)
