@@ -252,6 +252,23 @@ int b200yolo_greedy_nmm(const float* cand, const int* cand_src, const int* cand_
 int b200yolo_iou_cost_matrix(const float* tracks, const int* track_count, const float* det, const int* det_count,
                              int B, int T, int max_det, int fuse_score, float pad_cost, float* cost, void* stream);
 
+/* ---- N2: ByteTrack state arithmetic (supervision ByteTrack as the reference uses it, detect.py:22,557) --------------
+ * Batched over tracks, on state arrays that stay on the device: mean (capacity, 8) float64 [x, y, a, h, vx, vy, va, vh],
+ * cov (capacity, 8, 8) float64.  slots: (n) int32 rows of those arrays.
+ *   predict : STrack.multi_predict -- zero_vh[t] = 0: constant-velocity Kalman prediction; 1: vh zeroed first (tracks not
+ *             in the Tracked state); 2: no prediction (unconfirmed tracks / reading the current boxes).  tlbr (n,4)
+ *             float32 (optional) receives each track's box afterwards, ready to be the `tracks` argument of
+ *             b200yolo_iou_cost_matrix;
+ *   update  : KalmanFilter.update of track slots[t] with the detection box boxes[box_idx[t] * box_stride .. +4) (xyxy
+ *             float32, e.g. rows of the NMS output with box_stride = 6);
+ *   initiate: KalmanFilter.initiate of slots[t] from such a box (new tracks). */
+int b200yolo_kalman_predict(double* mean, double* cov, const int* slots, const int* zero_vh, int n, float* tlbr,
+                            void* stream);
+int b200yolo_kalman_update(double* mean, double* cov, const int* slots, const float* boxes, int box_stride,
+                           const int* box_idx, int n, void* stream);
+int b200yolo_kalman_initiate(double* mean, double* cov, const int* slots, const float* boxes, int box_stride,
+                             const int* box_idx, int n, void* stream);
+
 size_t b200yolo_workspace_bytes(int B, int cap);
 
 /* ---- host -> device staging of the source rows K1 references ------------------------------------

@@ -68,6 +68,9 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200yolo_iou_cost_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                          c_void_p, c_void_p]),
+    "b200yolo_kalman_predict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200yolo_kalman_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "b200yolo_kalman_initiate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "b200yolo_selftest_math": (c_int, [c_int, ctypes.c_uint64, c_void_p, c_void_p]),
     "b200yolo_copy2d_h2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
 }

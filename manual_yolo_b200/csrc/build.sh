@@ -9,12 +9,12 @@ COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include $ARCH"
 OUT="$ROOT/manual_yolo_b200/libb200yolo.so"
 mkdir -p "$HERE/_obj"
 # parity-critical fp32 kernels: no FMA contraction (every add/mul rounds like the torch CPU ops)
-for f in decode_filter nms postprocess_small assoc slices; do
+for f in decode_filter nms postprocess_small assoc slices track; do
   "$NVCC" $COMMON -fmad=false "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
 done
 for f in abi letterbox sort_topk roi; do
   "$NVCC" $COMMON "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
 done
 wait
-"$NVCC" -shared $ARCH -o "$OUT" "$HERE"/_obj/{abi,letterbox,decode_filter,sort_topk,nms,roi,postprocess_small,slices,assoc}.o
+"$NVCC" -shared $ARCH -o "$OUT" "$HERE"/_obj/{abi,letterbox,decode_filter,sort_topk,nms,roi,postprocess_small,slices,assoc,track}.o
 echo "built $OUT"

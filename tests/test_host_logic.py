@@ -367,3 +367,23 @@ def test_oracle_greedy_nmm_semantics():
     out, _ = slicing.greedy_nmm_postprocess_ref(q, "IOS", 0.5, class_agnostic=True)
     exp2 = torch.tensor([[0., 0., 80., 50., 0.9, 0.], [45., 0., 70., 50., 0.7, 0.]])            # C only overlaps the grown box
     assert torch.equal(torch.tensor(sorted(out.tolist())), exp2)
+
+
+def test_oracle_bytetrack_restatement_tracks_a_simple_scene():
+    """oracle/bytetrack.py sanity (no GPU): two objects crossing the frame keep their ids, a 10-frame occlusion is
+    bridged (lost -> re-activated, same id), a one-frame false positive never gets a confirmed id twice."""
+    from oracle import bytetrack as obt
+    trk = obt.ByteTrackRef()
+    ids = []
+    for f in range(40):
+        boxes = [[100 + 5 * f, 100, 160 + 5 * f, 180, 0.9]]
+        if not (15 <= f < 25):
+            boxes.append([800 - 4 * f, 300, 880 - 4 * f, 420, 0.8])
+        if f == 30:
+            boxes.append([1200, 600, 1250, 660, 0.7])
+        b = np.asarray(boxes, np.float32)
+        ids.append(trk.update_with_detections(b[:, :4], b[:, 4]).tolist())
+    assert all(r[0] == ids[0][0] and r[0] > 0 for r in ids)               # object A: one id throughout
+    b_ids = {r[1] for f, r in enumerate(ids) if not (15 <= f < 25) and len(r) > 1 and f != 30}
+    assert len(b_ids) == 1 and b_ids != {ids[0][0]}                       # object B: same id before and after the gap
+    assert trk.max_time_lost == 30 and trk.det_thresh == 0.35
