@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200yolo.so")
+LIB_PATH = os.environ.get("B200YOLO_LIB") or os.path.join(_HERE, "libb200yolo.so")   # env override: tuning experiments only
 
 
 class Level(Structure):

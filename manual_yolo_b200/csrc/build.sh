@@ -6,15 +6,16 @@ ROOT="$(cd "$HERE/../.." && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include $ARCH"
-OUT="$ROOT/manual_yolo_b200/libb200yolo.so"
-mkdir -p "$HERE/_obj"
+OUT="${B200YOLO_OUT:-$ROOT/manual_yolo_b200/libb200yolo.so}"     # (tuning experiments build variants side by side)
+OBJ="${B200YOLO_OBJ:-$HERE/_obj}"
+mkdir -p "$OBJ"
 # parity-critical fp32 kernels: no FMA contraction (every add/mul rounds like the torch CPU ops)
 for f in decode_filter nms postprocess_small assoc slices track; do
-  "$NVCC" $COMMON -fmad=false "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
+  "$NVCC" $COMMON -fmad=false "$@" -c "$HERE/$f.cu" -o "$OBJ/$f.o" &
 done
 for f in abi letterbox sort_topk roi; do
-  "$NVCC" $COMMON "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
+  "$NVCC" $COMMON "$@" -c "$HERE/$f.cu" -o "$OBJ/$f.o" &
 done
 wait
-"$NVCC" -shared $ARCH -o "$OUT" "$HERE"/_obj/{abi,letterbox,decode_filter,sort_topk,nms,roi,postprocess_small,slices,assoc,track}.o
+"$NVCC" -shared $ARCH -o "$OUT" "$OBJ"/{abi,letterbox,decode_filter,sort_topk,nms,roi,postprocess_small,slices,assoc,track}.o
 echo "built $OUT"

@@ -4,7 +4,7 @@
 // detect.py:541, yolo.py:361, pipe.py:179); arithmetic restated in oracle/letterbox.py
 // (SURVEY.md Appendix B.1).
 //
-// One CTA produces kRows consecutive output rows of one frame; thread t owns output pixels 4t..4t+3 of
+// One CTA produces kRows (8) consecutive output rows of one frame; thread t owns output pixels 4t..4t+3 of
 // every row, so its horizontal taps (double/float arithmetic exactly as cv::resize builds its tables)
 // are derived ONCE and stay in registers.  The (at most two) source rows each output row references are
 // staged in shared memory by the TMA engine (cp.async.bulk 1-D copies completing on an mbarrier;
@@ -81,8 +81,19 @@ __device__ __forceinline__ uint8_t lb_cast<uint8_t>(const float*, int v) { retur
 template <>
 __device__ __forceinline__ __half lb_cast<__half>(const float* lut, int v) { return __float2half_rn(lut[v]); }
 
-constexpr int kRows = 8;     // output rows per CTA
-constexpr int kStages = 2;   // ring slots: row r+1 is in flight while row r is blended (3 and 4 slots measured: no gain)
+#ifndef B200_LB_ROWS
+// Rows per CTA, measured on 64 frames 1920x1200 -> 640x640 (us per launch of the kernel ALONE): 1: 111.5, 2: 87.0,
+// 3: 82.4, 4: 76.8 (0.92 of the copy peak), 5: 78.7, 6: 78.2, 8: 79.0 (0.89), 16: 82.9, 32: 89.2.  The whole step
+// (letterbox concurrent with class filter -> post-processing -> ROI crops, two batches in flight) is fastest with 8:
+// 572 k frames/s against 570 k (6 rows) and 561 k (4 rows) -- the extra per-CTA set-up of short CTAs takes issue slots
+// from the latency-bound kernels running beside them.  8 it is: the pipeline is the product, not the kernel alone.
+#define B200_LB_ROWS 8
+#endif
+#ifndef B200_LB_STAGES
+#define B200_LB_STAGES 2
+#endif
+constexpr int kRows = B200_LB_ROWS;       // output rows per CTA
+constexpr int kStages = B200_LB_STAGES;   // ring slots: row r+1 is in flight while row r is blended
 
 struct RowInfo { int r0, r1, b0, b1; };   // b0 < 0 marks a padding row
 
