@@ -4,7 +4,7 @@ letterbox -> YOLOv8 Detect-head decode + confidence filter -> sort -> class-awar
 hand-written CUDA behind the C ABI of ``include/b200yolo.h`` (``libb200yolo.so``).  See DESIGN.md.
 """
 
-from . import classifier, geometry, handoff  # noqa: F401
+from . import classifier, geometry, handoff, tracking  # noqa: F401
 from .classifier import RankClassifier, load_rank_classifier  # noqa: F401
 from .api import (Candidates, DenseChain, Detections, Workspace, classify_preprocess, crop_resize_rois, decode_and_filter, filter_decoded,  # noqa: F401
                   gather_slice_detections, greedy_nmm, iou_cost_matrix, preprocess_slices,

@@ -219,7 +219,18 @@ __global__ void __launch_bounds__(kThreads) decode_filter_kernel(const Levels L,
 // anchor t: merge in class order, sigmoid, threshold.  Lazy DFL: only surviving anchors read their 64
 // box channels (coalesced across the owners of a dense tile), softmax expectation per side, decode, emit.
 // =================================================================================================
-constexpr int kVA = 256;          // anchors per CTA
+// Tuning hooks (defaults = the measured best; sweep recorded in profiles/README.md)
+#ifndef B200_K2_T
+#define B200_K2_T 256             // threads per CTA = anchors per CTA
+#endif
+#ifndef B200_K2_MINB
+#define B200_K2_MINB 4            // resident CTAs per SM the register budget is held to
+#endif
+#ifndef B200_K2_INFLIGHT
+#define B200_K2_INFLIGHT 8        // 128-bit loads issued per thread before the first compare
+#endif
+constexpr int kVA = B200_K2_T;    // anchors per CTA
+constexpr int kVL = B200_K2_INFLIGHT;
 
 struct FlatSegs {
   const float* ptr[B200YOLO_MAX_LEVELS];
@@ -229,7 +240,7 @@ struct FlatSegs {
 };
 
 template <bool RAW>
-__global__ void __launch_bounds__(256, 4) decode_vec_kernel(const FlatSegs S, const Levels L, int nc, int cls0,
+__global__ void __launch_bounds__(kVA, B200_K2_MINB) decode_vec_kernel(const FlatSegs S, const Levels L, int nc, int cls0,
                                                             float conf, const uint32_t* __restrict__ class_mask,
                                                             float* __restrict__ cand, int* __restrict__ cand_anchor,
                                                             int* __restrict__ cand_count, int cap) {
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(256, 4) decode_vec_kernel(const FlatSegs S, co
 
   // ---- phase 1: thread = (quarter q, 4 consecutive anchors); 128-bit loads, 8 in flight ----
   {
-    const int q = tid >> 6, t4 = (tid & 63) * 4;
+    const int q = tid / (kVA / 4), t4 = (tid % (kVA / 4)) * 4;
     const bool live = a_cta + t4 < scount;                    // segment counts are multiples of 4
     const int cq = (nc + kQ - 1) / kQ;
     const int c0 = q * cq, c1 = min(nc, c0 + cq);
@@ -257,10 +268,10 @@ __global__ void __launch_bounds__(256, 4) decode_vec_kernel(const FlatSegs S, co
     int j[4] = {c0, c0, c0, c0};
     if (live) {
       const float* p = sptr + (long long)b * sbs + (long long)(cls0 + c0) * scs + a_cta + t4;
-      for (int c = c0; c < c1; c += 8) {
-        float4 v[8];
+      for (int c = c0; c < c1; c += kVL) {
+        float4 v[kVL];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kVL; ++u) {
           if (c + u < c1) {
             asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
@@ -269,9 +280,9 @@ __global__ void __launch_bounds__(256, 4) decode_vec_kernel(const FlatSegs S, co
             v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
           }
         }
-        p += 8 * scs;
+        p += kVL * scs;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kVL; ++u) {
           if (v[u].x > m[0]) { m2[0] = m[0]; m[0] = v[u].x; j[0] = c + u; }
           if (v[u].y > m[1]) { m2[1] = m[1]; m[1] = v[u].y; j[1] = c + u; }
           if (v[u].z > m[2]) { m2[2] = m[2]; m[2] = v[u].z; j[2] = c + u; }
@@ -454,7 +465,7 @@ static int launch_vec(const Levels& L, int B, int nc, int cls0, float conf, cons
     }
   }
   dim3 grid((unsigned)((maxcount + kVA - 1) / kVA), B, S.n);
-  decode_vec_kernel<RAW><<<grid, 256, 0, stream>>>(S, L, nc, cls0, conf, class_mask, cand, cand_anchor, cand_count, cap);
+  decode_vec_kernel<RAW><<<grid, kVA, 0, stream>>>(S, L, nc, cls0, conf, class_mask, cand, cand_anchor, cand_count, cap);
   if (RAW && !defer_boxes) {
     const int amax = cap < A ? cap : A;               // an image has at most min(cap, A) stored survivors
     const int per_image = (amax + 63) / 64;           // blocks of 64 survivors

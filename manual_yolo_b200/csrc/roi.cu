@@ -268,8 +268,14 @@ constexpr int kFRows = 106;       // uint8 strip rows: source rows one vertical 
 constexpr int kPool = 1248;       // per-warp row-slot pool: 4 rows of <= 304 B, 3 of <= 416 B, 2 of <= 624 B, 1 of <= 1248 B
 constexpr int kRingMax = 4;       // rows in flight per warp
 constexpr uint32_t kRnd4 = 1u << (kPrec + 1);   // Pillow's 2^(PRECISION_BITS-1) rounding term, in the <<2 domain
-constexpr double kSegScale = 1.3; // two-segment launches: crops down-scaled by more than this run first
-constexpr int kSegMinRois = 1024; // ... when the launch holds at least this many ROIs (more than one wave of CTAs)
+#ifndef B200_K5_SEG_SCALE
+#define B200_K5_SEG_SCALE 1.3
+#endif
+#ifndef B200_K5_SEG_MIN
+#define B200_K5_SEG_MIN 1024
+#endif
+constexpr double kSegScale = B200_K5_SEG_SCALE; // two-segment launches: crops down-scaled by more than this run first
+constexpr int kSegMinRois = B200_K5_SEG_MIN;    // ... when the launch holds at least this many ROIs (more than one wave of CTAs)
 
 struct FastSmem {
   uint32_t xk[kFTaps][kS];        // horizontal weights << 2, transposed (conflict-free per warp)

@@ -218,3 +218,40 @@ def test_postprocess_dense_equals_stagewise_chain(cuda_dev):
             assert torch.equal(det.anchor[b, :k].cpu().long(), ref_idx[b])
             assert torch.equal(det.rows[b, :k].cpu()[:, 5], ref_out[b][:, 5])
             assert (det.rows[b, :k].cpu()[:, :5] - ref_out[b][:, :5]).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("splits,pipelined", [(2, True), (5, True), (3, False)])
+def test_dense_chain_sub_batches_equal_single_stream(cuda_dev, splits, pipelined):
+    """api.DenseChain (sub-batches of the images on their own streams; pipelined = filters back to back, each
+    sub-batch's tail forked under the next filter) == the single-stream chain, eagerly and as a CUDA graph."""
+    lv = geometry.level_shapes(640, 640)
+    B = 7
+    hd = synth.synth_head_dense(B, 80, seed=11).to(cuda_dev)
+    cands = m.decode_and_filter(hd, conf_thres=0.001, level_hw=lv, defer_boxes=True)
+    ws = m.Workspace(B, cands.cap, 300, cuda_dev)
+    ref = m.postprocess_dense(cands, ws, hd, level_hw=lv, iou_thres=0.7, max_det=300)
+    r_rows, r_anchor, r_count = ref.rows.clone(), ref.anchor.clone(), ref.count.clone()
+    dc = m.DenseChain(B, cands.cap, 300, cuda_dev, splits=splits, pipelined=pipelined)
+    for _ in range(2):
+        det = dc(hd, conf_thres=0.001, iou_thres=0.7, level_hw=lv)
+        torch.cuda.synchronize()
+        assert torch.equal(det.count, r_count) and torch.equal(dc.cand_count, cands.count)
+        for b in range(B):
+            k = int(r_count[b])
+            assert torch.equal(det.anchor[b, :k], r_anchor[b, :k]) and torch.equal(det.rows[b, :k], r_rows[b, :k])
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        dc(hd, conf_thres=0.001, iou_thres=0.7, level_hw=lv)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        dc(hd, conf_thres=0.001, iou_thres=0.7, level_hw=lv)
+    dc.det.rows.zero_(); dc.det.count.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(dc.det.count, r_count)
+    for b in range(B):
+        k = int(r_count[b])
+        assert torch.equal(dc.det.rows[b, :k], r_rows[b, :k])
