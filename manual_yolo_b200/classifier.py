@@ -4,8 +4,9 @@
 module only makes the hand-off runnable without Ultralytics installed --
 
 * ``load_rank_classifier(path)`` reads the Ultralytics checkpoint with a restricted unpickler: every
-  ``ultralytics.*`` class is replaced by an inert ``nn.Module`` shell (no Ultralytics code runs), anything outside
-  torch / collections / builtins containers is refused;
+  ``ultralytics.*`` class is replaced by an inert ``nn.Module`` shell (no Ultralytics code runs); beyond that only
+  an explicit allow-list resolves (tensor rebuild helpers, ``torch.nn`` layer classes, torchvision transform classes,
+  plain containers) -- any other global, in particular any function, is refused;
 * ``RankClassifier.forward_logits`` restates the four upstream module types on plain torch ops (``Conv`` =
   SiLU(BN(Conv2d)), ``Bottleneck``, ``C2f``, ``Classify``; ultralytics==8.3.176 ``nn/modules``), on whatever device the
   ROI batch lives on, fp32 like the reference (``runs/rank_classifier/args.yaml:42`` ``half: false``);
@@ -27,8 +28,28 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 _STRIDE2 = ("model.0", "model.1", "model.3", "model.5", "model.7")      # ckpt yaml: the five stride-2 Convs
-_ALLOWED_PREFIXES = ("torch", "collections", "builtins", "__builtin__", "numpy", "_codecs", "pathlib", "copyreg", "datetime",
-                     "torchvision.transforms", "PIL")
+# Globals a YOLOv8 classification checkpoint may reference: tensor / storage rebuild helpers, torch.nn layer classes,
+# the torchvision transform objects stored with the model, plain containers.  Everything else is refused -- in
+# particular every callable that could run code or touch files (torch.load / hub / cpp_extension, os, subprocess ...).
+_ALLOWED_MODULE_PREFIXES = ("torch.nn.modules.", "torchvision.transforms.")
+_ALLOWED_GLOBALS = {
+    "collections": {"OrderedDict", "defaultdict"},
+    "builtins": {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "complex", "slice", "range"},
+    "__builtin__": {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "complex", "slice", "range"},
+    "torch": {"Size", "device", "dtype", "Tensor", "FloatStorage", "HalfStorage", "BFloat16Storage", "DoubleStorage",
+              "LongStorage", "IntStorage", "ShortStorage", "CharStorage", "ByteStorage", "BoolStorage", "float16", "float32",
+              "float64", "bfloat16", "int64", "int32", "int16", "int8", "uint8", "bool"},
+    "torch._utils": {"_rebuild_tensor_v2", "_rebuild_parameter", "_rebuild_parameter_with_state", "_rebuild_tensor"},
+    "torch.storage": {"TypedStorage", "UntypedStorage", "_load_from_bytes"},
+    "torch.nn.parameter": {"Parameter", "Buffer"},
+    "numpy": {"dtype", "ndarray"},
+    "numpy.core.multiarray": {"_reconstruct", "scalar"},
+    "numpy._core.multiarray": {"_reconstruct", "scalar"},
+    "_codecs": {"encode"},
+    "pathlib": {"PosixPath", "PurePosixPath", "WindowsPath", "PureWindowsPath", "Path"},
+    "datetime": {"datetime", "date", "timedelta"},
+    "copyreg": {"_reconstructor"},
+}
 
 
 class _Shell(nn.Module):
@@ -53,11 +74,13 @@ class _RestrictedUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.split(".")[0] == "ultralytics":
             return _shell_class(module, name)
-        if module in ("builtins", "__builtin__") and name in ("eval", "exec", "compile", "open", "__import__", "getattr",
-                                                              "setattr", "delattr", "input", "breakpoint"):
-            raise pickle.UnpicklingError(f"rank classifier checkpoint references builtin {name}: refused")
-        if module.startswith(_ALLOWED_PREFIXES):
+        if name in _ALLOWED_GLOBALS.get(module, ()) and module != "torch.storage" or \
+                (module == "torch.storage" and name in ("TypedStorage", "UntypedStorage")):
             return super().find_class(module, name)
+        if module.startswith(_ALLOWED_MODULE_PREFIXES) and "." not in name and not name.startswith("_"):
+            obj = super().find_class(module, name)
+            if isinstance(obj, type):                      # layer / transform / enum CLASSES only, never functions
+                return obj
         raise pickle.UnpicklingError(f"rank classifier checkpoint references {module}.{name}: refused")
 
 

@@ -1,4 +1,5 @@
 """Host-side logic of the product (no GPU): geometry mirrors, masks, sharding, record schema."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -276,6 +277,7 @@ def test_product_classifier_from_arrays_matches_oracle(golden_dir):
 
 
 @pytest.mark.reference
+@pytest.mark.skipif(not os.path.exists("/root/reference/rank_classifier.pt"), reason="reference checkpoint not on this box")
 def test_product_classifier_loads_reference_checkpoint(golden_dir):
     """rank_classifier.pt (detect.py:21) through the restricted unpickler: no Ultralytics, no oracle."""
     import pickle
@@ -295,6 +297,13 @@ def test_product_classifier_loads_reference_checkpoint(golden_dir):
             return (os.system, ("true",))
     with pytest.raises(pickle.UnpicklingError):
         pc._RestrictedUnpickler(io.BytesIO(pickle.dumps(Evil()))).load()
+    # ... including functions that live in allowed packages (only layer / transform classes and rebuild helpers resolve)
+    for mod, name in (("torch", "load"), ("torch.hub", "load"), ("builtins", "eval"), ("builtins", "getattr"),
+                      ("torch.nn.modules.module", "_addindent"), ("torchvision.transforms.functional", "to_pil_image"),
+                      ("torch.storage", "_load_from_bytes"), ("os", "system")):
+        with pytest.raises(pickle.UnpicklingError):
+            pc._RestrictedUnpickler(io.BytesIO(b"")).find_class(mod, name)
+    assert pc._RestrictedUnpickler(io.BytesIO(b"")).find_class("torch.nn.modules.conv", "Conv2d") is torch.nn.Conv2d
 
 
 def test_div255_two_constant_form_is_exact():
