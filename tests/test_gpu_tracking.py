@@ -110,3 +110,36 @@ def test_kalman_kernels_against_numpy_filter(cuda_dev):
         w = mu[2] * mu[3]
         exp = np.array([mu[0] - w / 2, mu[1] - mu[3] / 2, mu[0] - w / 2 + w, mu[1] - mu[3] / 2 + mu[3]], np.float32)
         assert np.allclose(tlbr[i].cpu().numpy(), exp, rtol=1e-6, atol=1e-4)
+
+
+def test_bytetrack_empty_frames_and_capacity(cuda_dev):
+    """Frames without detections (tracks go lost, then are removed after the buffer) follow the restatement; running out
+    of track slots raises instead of dropping tracks silently."""
+    frames = _sequence(n_frames=50, n_obj=6, seed=3)
+    for f in list(range(12, 16)) + list(range(30, 50)):
+        frames[f] = np.zeros((0, 6), np.float32)
+    max_det = 32
+    kw = dict(lost_track_buffer=8)
+    trk = tracking.ByteTrack(device=cuda_dev, capacity=64, max_det=max_det, **kw)
+    ref = obt.ByteTrackRef(**kw)
+    for f, rows in enumerate(frames):
+        n = rows.shape[0]
+        pad = torch.zeros((1, max_det, 6))
+        pad[0, :n] = torch.from_numpy(rows)
+        det = m.Detections(pad.to(cuda_dev), torch.zeros((1, max_det), dtype=torch.int32, device=cuda_dev),
+                           torch.tensor([n], dtype=torch.int32, device=cuda_dev))
+        got = trk.update(det, 0)
+        exp = ref.update_with_detections(rows[:, :4], rows[:, 4])
+        assert got.tolist() == exp.tolist(), f
+        assert len(trk.tracked) == len(ref.tracked_tracks) and len(trk.lost) == len(ref.lost_tracks), f
+    assert not trk.tracked and not trk.lost                               # everything timed out during the empty tail
+    assert len(trk._free) == 64                                           # ... and every slot came back
+    small = tracking.ByteTrack(device=cuda_dev, capacity=3, max_det=max_det)
+    rows = _sequence(n_frames=1, n_obj=10, seed=5)[0]
+    rows[:, 4] = 0.9
+    pad = torch.zeros((1, max_det, 6))
+    pad[0, :rows.shape[0]] = torch.from_numpy(rows)
+    det = m.Detections(pad.to(cuda_dev), torch.zeros((1, max_det), dtype=torch.int32, device=cuda_dev),
+                       torch.tensor([rows.shape[0]], dtype=torch.int32, device=cuda_dev))
+    with pytest.raises(RuntimeError, match="capacity"):
+        small.update(det, 0)
