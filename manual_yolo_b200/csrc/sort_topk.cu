@@ -164,17 +164,43 @@ __global__ void __launch_bounds__(NT) sort_topk_kernel(const float* __restrict__
 constexpr int kSelK = 2048;
 constexpr int kPre = 512;          // entries whose boxes b200yolo_postprocess_dense decodes ahead of the NMS (one NMS window)
 
+// Bitonic network over the kSelK = 2048 keys in s[], 1024 threads.  Thread t keeps elements 2t and 2t+1 in registers:
+// a compare-exchange at distance j <= 32 pairs element i with i ^ j, i.e. the same register of lane ^ (j / 2) (or the
+// thread's other register for j = 1) -- 51 of the network's 66 steps are warp shuffles without a CTA barrier; only the
+// 15 steps at distance >= 64 go through shared memory.
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void bitonic_reg_steps(uint64_t& e0, uint64_t& e1, int i0, int k, int jstart) {
+  const bool up = (i0 & k) == 0;
+  for (int j = jstart; j >= 2; j >>= 1) {
+    const uint64_t p0 = shfl_xor_u64(e0, j >> 1), p1 = shfl_xor_u64(e1, j >> 1);
+    const bool keep_min = ((i0 & j) == 0) == up;
+    e0 = (keep_min == (p0 < e0)) ? p0 : e0;
+    e1 = (keep_min == (p1 < e1)) ? p1 : e1;
+  }
+  if ((e0 > e1) == up) { const uint64_t t = e0; e0 = e1; e1 = t; }
+}
 __device__ __forceinline__ void bitonic_sort_2048(uint64_t* s, int tid, int nt) {
-  for (int k = 2; k <= kSelK; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < kSelK / 2; t += nt) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-        const uint64_t a = s[i], c = s[l];
-        if ((a > c) == ((i & k) == 0)) { s[i] = c; s[l] = a; }
-      }
+  (void)nt;                                                   // launched with kSelK / 2 threads
+  const int i0 = 2 * tid;
+  uint64_t e0 = s[i0], e1 = s[i0 + 1];
+  for (int k = 2; k <= 64; k <<= 1) bitonic_reg_steps(e0, e1, i0, k, k >> 1);
+  for (int k = 128; k <= kSelK; k <<= 1) {
+    s[i0] = e0; s[i0 + 1] = e1;
+    __syncthreads();
+    for (int j = k >> 1; j >= 64; j >>= 1) {
+      const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1)), l = i | j;
+      const uint64_t a = s[i], c = s[l];
+      if ((a > c) == ((i & k) == 0)) { s[i] = c; s[l] = a; }
       __syncthreads();
     }
+    e0 = s[i0]; e1 = s[i0 + 1];
+    bitonic_reg_steps(e0, e1, i0, k, 32);
   }
+  s[i0] = e0; s[i0 + 1] = e1;
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __restrict__ cand,
@@ -188,7 +214,7 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
   uint64_t* src = sB + kSelK;                                     // [cap] all keys (shared memory, or the workspace)
   __shared__ uint32_t hist[256];
   __shared__ unsigned long long sel_prefix;
-  __shared__ int sel_k, cursor;
+  __shared__ int sel_k, cursor, sel_done;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = min(min(cand_count[b], cap), B200YOLO_MAX_SORT);
   const int n_out = min(max(n, 0), max_nms);
@@ -227,6 +253,9 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
     for (int shift = 56; shift >= 16; shift -= 8) {
       if (tid < 256) hist[tid] = 0;
       __syncthreads();
+      // (scores cluster: most keys of a warp fall into a few bins -- one shared-memory atomic per distinct bin and warp)
+      // (atomicAdd(.., 1) on shared memory compiles to ATOMS.POPC.INC, which already merges the lanes of a warp that
+      // hit the same bin: explicit warp aggregation -- match_any, or a uniform-warp test -- measured 10-18 us slower)
       for (int i = tid; i < n; i += NT) {
         const uint64_t k = src[i];
         if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(k >> shift) & 0xff], 1u);
@@ -250,6 +279,7 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
             if (run < (uint32_t)kk && (uint32_t)kk <= run + c[j]) {
               sel_prefix = (prefix << 8) | (unsigned long long)(lane * 8 + j);
               sel_k = kk - (int)run;
+              sel_done = (uint32_t)kk == run + c[j];    // the whole bin is taken: the lower digits decide nothing
             }
             run += c[j];
           }
@@ -258,6 +288,10 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
       __syncthreads();
       prefix = sel_prefix;
       kk = sel_k;
+      if (sel_done) {                                   // (with distinct scores: after the 32 score bits, 4 passes of 6)
+        prefix = (prefix << (shift - 16)) | ((1ull << (shift - 16)) - 1ull);
+        break;
+      }
     }
     // keys are unique in their top 48 bits (score, anchor): exactly kSelK keys satisfy (key >> 16) <= prefix.
     // The threshold goes to the header: the box decode of b200yolo_postprocess_dense selects by it, in slot order.
