@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
     for (int s = 0; s < wn; s += kChunk) {
       const int m = min(kChunk, wn - s);
       // ---- (A) intra-chunk mask: thread -> row i = t/16, columns j = (t%16)*4 .. +3 ----
+      if (tid < 128) cmask[tid] = 0ull;                    // phase (C)'s class buckets: idle until this chunk's (B) is done
+      if (tid == 128 % NT) always_s = 0ull;
       for (int t = tid; t < kChunk * 16; t += NT) {
         const int i = t >> 4, jg = t & 15;
         unsigned nib = 0;
@@ -206,10 +208,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
       // kept boxes per later box instead of up to 64.
       const unsigned long long kept = kept_bits_s;
       if (kept && s + kChunk < wn) {
-        if (tid < 128) cmask[tid] = 0ull;
-        if (tid == 128 % NT) always_s = 0ull;
-        __syncthreads();
-        if (tid < kChunk && ((kept >> tid) & 1ull)) {
+        if (tid < kChunk && ((kept >> tid) & 1ull)) {     // (cmask / always_s were cleared in phase (A))
           const int mi = meta[s + tid];
           if (mi < 0) atomicOr(&always_s, 1ull << tid);
           else atomicOr(&cmask[mi & 127], 1ull << tid);

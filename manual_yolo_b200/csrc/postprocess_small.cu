@@ -250,20 +250,31 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
       if (lane == 0) sm.rem_bits[wid] = bits;
     }
     __syncthreads();
-    if (tid == 0) {
+    // resolve of the chunk by warp 0 as a fixed-point iteration (see nms.cu phase (B)): K = alive & ~S(K), S(K) = union
+    // of the mask rows of the boxes in K; two REDUX.OR per step, box j final after its suppression chain's length
+    if (tid < 32) {
+      const unsigned long long r0 = lane < m ? sm.mask[lane] : 0ull, r1 = lane + 32 < m ? sm.mask[lane + 32] : 0ull;
       const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-      unsigned long long alive = valid & ~(((unsigned long long)sm.rem_bits[1] << 32) | sm.rem_bits[0]);
-      unsigned long long kept = 0;
-      int kc = sm.kcount;
-      while (alive && kc < max_det) {
-        const int i = __ffsll((long long)alive) - 1;
-        kept |= 1ull << i;
-        keep[kc++] = s + i;
-        alive &= ~sm.mask[i];
-        alive &= ~(1ull << i);
+      const unsigned long long alive = valid & ~(((unsigned long long)sm.rem_bits[1] << 32) | sm.rem_bits[0]);
+      unsigned long long K = alive;
+      for (;;) {
+        const unsigned long long sl = (((K >> lane) & 1ull) ? r0 : 0ull) | (((K >> (lane + 32)) & 1ull) ? r1 : 0ull);
+        const unsigned long long S = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(sl >> 32)) << 32) |
+                                     __reduce_or_sync(0xffffffffu, (unsigned)sl);
+        const unsigned long long Kn = alive & ~S;
+        if (Kn == K) break;
+        K = Kn;
       }
-      sm.kept_bits = kept;
-      sm.kcount = kc;
+      const int kc = sm.kcount;
+      int over = kc + __popcll(K) - max_det;             // keeps beyond max_det: drop the last ones (score order)
+      while (over > 0) { K &= ~(1ull << (63 - __clzll((long long)K))); --over; }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                      // the chunk's keeps, in order
+        const int i = lane + 32 * h;
+        if ((K >> i) & 1ull) keep[kc + __popcll(K & ((1ull << i) - 1ull))] = s + i;
+      }
+      __syncwarp();
+      if (lane == 0) { sm.kept_bits = K; sm.kcount = kc + __popcll(K); }
     }
     __syncthreads();
     if (sm.kcount >= max_det) break;
