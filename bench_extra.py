@@ -113,7 +113,7 @@ def config3(dev, B=256, nc=80, cpu_images=4):
     del g1
     # forked: every sub-batch's whole chain on its own stream; pipelined: class filters back to back on one stream, each
     # sub-batch's select-sort -> decode -> NMS forked onto a high-priority stream as soon as its own filter is done
-    for splits, pipelined in ((2, True), (4, True), (4, False)):
+    for splits, pipelined in ((2, True), (4, False), (8, False)):
         dc = m.DenseChain(B, cands2.cap, 300, dev, splits=splits, pipelined=pipelined)
         gd = graphed(lambda: dc(head, conf_thres=0.001, iou_thres=0.7, level_hw=lv))
         r = timed(lambda: gd.replay(), flush=flush)

@@ -484,11 +484,11 @@ class DenseChain:
     ``pipelined=True``: the class filters of the sub-batches run back to back on the caller's stream and sub-batch s's
     select-sort -> decode -> NMS start on a high-priority stream as soon as ITS filter has finished.  Measured SLOWER
     than launching every sub-batch's whole chain at once (config 3, one CUDA graph: 338 / 353 us with 2 / 4 sub-batches
-    against 323 us forked and 329 us single-stream): the per-image kernels are latency-bound but not light -- a
+    against 323 us forked and 329 us single-stream at the time): the per-image kernels are latency-bound but not light -- a
     select-sort CTA holds 1024 of an SM's 2048 thread slots and 84 KB of its shared memory -- so they take whole SMs
     away from the streaming filter instead of hiding under it.  Kept as an option; the default is the forked form."""
 
-    def __init__(self, B, cap, max_det, device, splits=2, pipelined=False):
+    def __init__(self, B, cap, max_det, device, splits=8, pipelined=False):
         splits = max(1, min(int(splits), B))
         self.pipelined = bool(pipelined) and splits > 1
         self.B, self.cap, self.max_det, self.device = B, cap, max_det, torch.device(device)
