@@ -17,8 +17,9 @@
 // filter), so neither the gather of the sorted rows nor the suppression sweep touches the rest.  A window lives in
 // shared memory (21 B per box); the kept boxes of earlier windows (<= max_det, 20 B each) stay resident and a new
 // window is first tested against them.  Inside a window boxes are processed in chunks of 64 (sorted order): (A) the
-// 64x64 intra-chunk IoU bitmask is built in parallel (4 pairs per thread, rows merged with warp shuffles), (B) one
-// thread resolves the chunk serially over the mask words (ffs over the alive bits), (C) the chunk's kept boxes
+// 64x64 intra-chunk IoU bitmask is built in parallel (4 pairs per thread, rows merged with warp shuffles), (B) warp 0
+// resolves the chunk as a fixed-point iteration over the mask rows (K = alive & ~S(K): 2-4 warp-wide steps of two
+// REDUX.OR each, instead of a serial sweep with one dependent load per suppressing box), (C) the chunk's kept boxes
 // are applied to every later box of the window in parallel.  ~19 KB of shared memory per CTA: several images per
 // SM, so a batch of 256 images is one wave.  Compiled with -fmad=false.
 

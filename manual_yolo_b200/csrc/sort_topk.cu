@@ -15,7 +15,9 @@
 //              32-key row); passes whose digit is uniform across the image are skipped.
 //   cap > 2048 (dense regime): sort_select_kernel -- greedy NMS consumes the sorted list from the top and stops
 //              at max_det keeps, so only the best kSelK = 2048 keys are put in order: a 6-pass MSD radix SELECT
-//              finds the kSelK-th smallest key, the keys up to it are compacted and bitonic-sorted.  The number
+//              finds the kSelK-th smallest key (early exit when the selected bin is taken whole), the keys up to it
+//              are compacted and bitonic-sorted (two keys per thread in registers: the steps at distance <= 32 are
+//              warp shuffles, only the 15 steps at distance >= 64 go through shared memory).  The number
 //              of sorted entries goes to the workspace header; if the NMS ever runs out of them before max_det
 //              keeps, it raises a per-image flag and b200yolo_nms re-runs that image with the full sort above
 //              (exact in every case, one cheap path in the common one).
