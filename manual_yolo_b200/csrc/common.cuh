@@ -17,6 +17,24 @@
     if (!(cond)) return (code);  \
   } while (0)
 
+// Checked build (-DB200_CHECKS, libb200yolo_checked.so; tools/checked.sh): device-side assertions on every
+// shared-memory ring / strip / key-array index and every global store index the kernels compute.  A failed check
+// prints its location and traps (the launch fails with a CUDA error).  compute-sanitizer is closed on the build pool;
+// this is the stand-in: the whole GPU test suite is run against the checked library.  No-ops in the product build.
+#ifdef B200_CHECKS
+#include <cstdio>
+#define B200_CHECK(cond)                                                                          \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      printf("B200_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,   \
+             (int)blockIdx.x, (int)threadIdx.x);                                                  \
+      __trap();                                                                                   \
+    }                                                                                             \
+  } while (0)
+#else
+#define B200_CHECK(cond) do { } while (0)
+#endif
+
 static inline int b200_launch_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? B200YOLO_OK : (int)e;

@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
     uint8_t* d1 = d0 + p.row_smem;
     const uint8_t* g0 = frame + (int64_t)ri.r0 * p.pitch;
     const uint8_t* g1 = frame + (int64_t)ri.r1 * p.pitch;
+    B200_CHECK(s >= 0 && s < kStages && nbytes <= p.row_smem);                 // the staged span fits its ring slot
+    B200_CHECK(ri.r0 >= 0 && ri.r0 < p.H && ri.r1 >= 0 && ri.r1 < p.H);        // source rows of this frame / window
     if (p.bulk_ok) {
+      B200_CHECK(((reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(g1) | (uintptr_t)nbytes) & 15) == 0);
       if (tid == 0) {
         b200::mbar_expect_tx(&bar[s], need1 ? 2u * nbytes : (uint32_t)nbytes);
         b200::bulk_g2s(d0, g0, nbytes, &bar[s]);
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
   };
 
   OutCursor<OutT> cur;
+  B200_CHECK(oy0 + nrows <= p.outH && (!have || ox0 + npx <= p.outW));         // this thread's output pixels exist
   if (have) cur.init(p, b, oy0, ox0, npx);
   const OutT padv = lb_cast<OutT>(lut, p.pad_value);
   unsigned uses = 0;                         // bit s = parity of completed phases of ring slot s (interior rows only)
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
         // exact integer decimation (weights 2048/0 on both axes): the output IS a source pixel
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          B200_CHECK(off[k] >= 0 && (off[k] & ~3) + 8 <= p.row_smem);
           const uint32_t* w = reinterpret_cast<const uint32_t*>(row0 + (off[k] & ~3));
           const uint32_t lo = __funnelshift_r(w[0], w[1], (off[k] & 3) * 8);
           v[k][0] = lb_cast<OutT>(lut, (int)(lo & 0xff));
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint32_t lo, hi;
+          B200_CHECK(off[k] >= 0 && ((off[k] >> 2) + 3) * 4 <= p.row_smem);      // load6 reads three words
           load6(row0, off[k], lo, hi);
           int S0[3], S1[3];
           S0[0] = (int)(lo & 0xff) * a0[k] + (int)(lo >> 24) * a1[k];

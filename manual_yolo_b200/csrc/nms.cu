@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
         const int r = r_lo + (q >> 2), sd = q & 3;
         const bool act = r < wn;
         const int slot = act ? orow[w0 + r] : 0;
+        B200_CHECK(slot >= 0 && slot < min(cand_count[b], cap));
         const b200::AnchorRef ar = b200::anchor_ref(L, b, act ? cand_anchor[(int64_t)b * cap + slot] : 0);
         const float d = act ? b200::dfl_side(ar.p + (long long)(sd * b200::kReg) * ar.cs, ar.cs) : 0.f;
         const int q0 = lane & ~3;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
         const unsigned long long kept = kept_bits_s;
         if (tid < kChunk && ((kept >> tid) & 1ull)) {
           const int r = kcount_s - __popcll(kept) + __popcll(kept & ((1ull << tid) - 1ull));
+          B200_CHECK(r >= 0 && r < max_det && s + tid < wn);
           keep[r] = w0 + s + tid;
           kbox[r] = box[s + tid];
           kmeta[r] = meta[s + tid];
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(NT) nms_kernel(const float* __restrict__ cand,
   if (scale) { gain = scale[b * 5 + 0]; padx = scale[b * 5 + 1]; pady = scale[b * 5 + 2]; w0s = scale[b * 5 + 3]; h0s = scale[b * 5 + 4]; }
   for (int r = tid; r < kc; r += NT) {
     const int slot = orow[keep[r]];
+    B200_CHECK(keep[r] >= 0 && keep[r] < n && slot >= 0 && slot < min(cand_count[b], cap));
     const float* row = crow + (int64_t)slot * 6;
     float x1 = row[0], y1 = row[1], x2 = row[2], y2 = row[3];
     if (scale) {

@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
 #pragma unroll
       for (int h = 0; h < 2; ++h) {                      // the chunk's keeps, in order
         const int i = lane + 32 * h;
+        B200_CHECK(!((K >> i) & 1ull) || (kc + __popcll(K & ((1ull << i) - 1ull)) < max_det && s + i < n_nms));
         if ((K >> i) & 1ull) keep[kc + __popcll(K & ((1ull << i) - 1ull))] = s + i;
       }
       __syncwarp();
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(NT) postprocess_small_kernel(const Levels L, i
   if (scale) { gain = scale[b * 5 + 0]; padx = scale[b * 5 + 1]; pady = scale[b * 5 + 2]; w0 = scale[b * 5 + 3]; h0 = scale[b * 5 + 4]; }
   for (int r = tid; r < kc; r += NT) {
     const int slot = sm.order[keep[r]];
+    B200_CHECK(keep[r] >= 0 && keep[r] < n_nms && slot >= 0 && slot < kCapMax);
     const float* row = sm.rows[slot];
     float x1 = row[0], y1 = row[1], x2 = row[2], y2 = row[3];
     if (scale) {

@@ -421,6 +421,10 @@ __device__ __forceinline__ void hpass(FastSmem& sm, const FastTile& t, int xo0, 
       if (ji < rows) {
         if (elect_one()) {
           const uint32_t nb = (phi + span + 15u) & ~15u;
+          B200_CHECK(s < nslots && s * rstride + nb <= (uint32_t)kPool);                 // the copy stays inside the slot pool
+          B200_CHECK(reinterpret_cast<const uint8_t*>(gi - phi) >= t.frames &&
+                     reinterpret_cast<const uint8_t*>(gi - phi) + nb <= t.buf_hi);       // ... and inside the caller's buffer
+          B200_CHECK(((gi - phi) & 15u) == 0 && ((ring_a + s * rstride) & 15u) == 0);    // bulk-copy alignment
           b200::mbar_expect_tx_addr(bar_a + 8u * s, nb);
           b200::bulk_g2s_addr(ring_a + s * rstride, reinterpret_cast<const void*>(gi - phi), nb, bar_a + 8u * s);
         }
@@ -434,6 +438,9 @@ __device__ __forceinline__ void hpass(FastSmem& sm, const FastTile& t, int xo0, 
     for (uint32_t j = wid; j < rows; j += kFWarps) {
       b200::mbar_wait_addr(bar_a + 8u * sidx, parity);
       const uint8_t* rb = ring + sidx * rstride + ph;
+      // the widest tap window read (zero-weight taps included) ends inside the ring array + its slack
+      B200_CHECK(rb + max(xo0, xo1) + 3 * (T - 1) + 2 < &sm.ring[0][0] + kFWarps * kPool + (int)sizeof(sm.slack));
+      B200_CHECK(so + 2 * kS + 32 < &sm.strip[0][0][0] + sizeof(sm.strip) && so >= &sm.strip[0][0][0]);
       hrow<T>(rb + xo0, rb + xo1, k0, k1, so);
       __syncwarp();                                          // every lane is done with this slot before it is refilled
       issue(sidx);
@@ -453,6 +460,8 @@ __device__ __forceinline__ void hpass(FastSmem& sm, const FastTile& t, int xo0, 
         for (int u = 0; u < 4; ++u) dw[u] = load_word_guarded(g - ph + ck * 16 + 4 * u, t.frames, t.buf_hi);
       }
       __syncwarp();
+      B200_CHECK(ring + ph + max(xo0, xo1) + 3 * (T - 1) + 2 < &sm.ring[0][0] + kFWarps * kPool + (int)sizeof(sm.slack));
+      B200_CHECK(so + 2 * kS + 32 < &sm.strip[0][0][0] + sizeof(sm.strip) && so >= &sm.strip[0][0][0]);
       hrow<T>(ring + ph + xo0, ring + ph + xo1, k0, k1, so);
       __syncwarp();
     }
@@ -475,6 +484,9 @@ __device__ __forceinline__ void vpass(FastSmem& sm, int t0, int t1, int rmin, fl
   const uint32_t* kq = &sm.yk[t0 + rsel][0];
   for (int yy = t0 + rsel; yy < t1; yy += 4, o += 4 * kS, ybp += 4 * 2, kq += 4 * kFKy) {
     const uint8_t* sp = spb + *ybp * (3 * kS);
+    // every tap row read (zero-weight ones included) lies inside the strip; the 4 outputs inside the ROI's plane
+    B200_CHECK(sp >= &sm.strip[0][0][0] && sp + (T - 1) * (3 * kS) + 3 < &sm.strip[0][0][0] + sizeof(sm.strip));
+    B200_CHECK(o >= out && o + 3 < out + 3 * kS * kS);
     uint32_t kv[((T + 3) / 4) * 4];
 #pragma unroll
     for (int i = 0; i < (T + 3) / 4; ++i) {

@@ -306,13 +306,17 @@ __global__ void __launch_bounds__(1024, 2) sort_select_kernel(const float* __res
       int pos = 0;
       if (lane == 0 && bal) pos = atomicAdd(&cursor, __popc(bal));
       pos = __shfl_sync(0xffffffffu, pos, 0);
+      B200_CHECK(!in || pos + __popc(bal & ((1u << lane) - 1u)) < kSelK);     // exactly kSelK keys pass the threshold
       if (in) sB[pos + __popc(bal & ((1u << lane) - 1u))] = k;
     }
     __syncthreads();
   }
   bitonic_sort_2048(sB, tid, NT);
   const int m = min(n_out, kSelK);
-  for (int r = tid; r < m; r += NT) orow[r] = (int)(sB[r] & 0xffff);
+  for (int r = tid; r < m; r += NT) {
+    B200_CHECK((int)(sB[r] & 0xffff) < n && (r == 0 || sB[r - 1] < sB[r]));      // a slot of this image, keys ascending
+    orow[r] = (int)(sB[r] & 0xffff);
+  }
   if (tid == 0 && n > kPre) {
     // threshold of the kPre best entries: the box decode ahead of the NMS takes exactly those (in slot order)
     const unsigned long long t = sB[min(m, kPre) - 1] >> 16;
