@@ -281,6 +281,16 @@ __global__ void __launch_bounds__(256, 4) letterbox_kernel(const LbParams p) {
     const int s = r % kStages;
     const RowInfo ri = rows[r];
     // slot (r-1) % kStages was released by the barrier that ended row r-1: refill it with row r+kStages-1
+#ifdef B200_CHECKS
+    if (p.bulk_ok && r >= 1 && r + kStages - 1 < nrows) {
+      // poison the released slot before its refill is issued: a blend that ran ahead of the refill's completion would
+      // read 0xA5 bytes, and the parity tests compare bit for bit
+      uint8_t* d = smem + (size_t)((r + kStages - 1) % kStages) * 2 * p.row_smem;
+      for (int i = tid * 4; i < 2 * p.row_smem; i += (int)blockDim.x * 4) *reinterpret_cast<uint32_t*>(d + i) = 0xA5A5A5A5u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+#endif
     if (r + kStages - 1 < nrows) prefetch(r + kStages - 1, (r + kStages - 1) % kStages);
     OutT v[4][3];
     if (ri.b0 < 0 || nbytes <= 0) {                  // CTA-uniform: padding row / chunk fully in the side padding

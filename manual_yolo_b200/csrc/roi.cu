@@ -443,6 +443,13 @@ __device__ __forceinline__ void hpass(FastSmem& sm, const FastTile& t, int xo0, 
       B200_CHECK(so + 2 * kS + 32 < &sm.strip[0][0][0] + sizeof(sm.strip) && so >= &sm.strip[0][0][0]);
       hrow<T>(rb + xo0, rb + xo1, k0, k1, so);
       __syncwarp();                                          // every lane is done with this slot before it is refilled
+#ifdef B200_CHECKS
+      // poison the consumed slot before its refill is issued: a read that ran ahead of the refill's completion (a
+      // wrong parity, a missing wait) would resample 0xA5 bytes, and the parity tests compare bit for bit
+      for (uint32_t o = lane * 4; o < rstride; o += 128) *reinterpret_cast<uint32_t*>(ring + sidx * rstride + o) = 0xA5A5A5A5u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+#endif
       issue(sidx);
       so += kFWarps * 3 * kS;
       ph = (ph + dph) & 15u;
