@@ -90,3 +90,20 @@ def test_sanitize_cases_run_clean(cuda_dev):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_cases.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "sanitize cases ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_sanitize_cases_run_clean_under_the_checked_build(cuda_dev):
+    """The same cases against libb200yolo_checked.so (-DB200_CHECKS: device-side assertions on every ring / strip /
+    key-array index, bulk-copy range and alignment, output index; TMA ring slots poisoned between last read and refill).
+    A failed assertion traps -> CUDA error -> non-zero exit.  Built by __graft_entry__.build() / tools/checked.sh."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "manual_yolo_b200", "libb200yolo_checked.so")
+    assert os.path.exists(lib), "run __graft_entry__.build() (or tools/checked.sh build) first"
+    env = dict(os.environ, B200YOLO_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_cases.py")], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0 and "sanitize cases ok" in r.stdout and "B200_CHECK failed" not in r.stdout, \
+        r.stdout[-2000:] + r.stderr[-2000:]

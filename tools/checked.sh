@@ -6,11 +6,10 @@
 set -uo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 cd "$ROOT"
-LIB="$ROOT/scratch/checked/libb200yolo_checked.so"
+LIB="$ROOT/manual_yolo_b200/libb200yolo_checked.so"
 case "${1:-build}" in
   build)
-    mkdir -p scratch/checked/obj
-    B200YOLO_OUT="$LIB" B200YOLO_OBJ="$ROOT/scratch/checked/obj" bash manual_yolo_b200/csrc/build.sh -DB200_CHECKS
+    B200YOLO_OUT="$LIB" B200YOLO_OBJ="$ROOT/manual_yolo_b200/csrc/_obj_checked" bash manual_yolo_b200/csrc/build.sh -DB200_CHECKS
     ;;
   run)
     [ -f "$LIB" ] || { echo "build first"; exit 1; }
