@@ -200,7 +200,11 @@ def test_reference_helpers_golden(golden_dir):
     for x1, y1, x2, y2, pad, shape in g["safe_crop_shapes"]:
         crop = oboxes.safe_crop_ref(frame, x1, y1, x2, y2, pad=pad)
         assert (None if crop is None else list(crop.shape[:2])) == shape, (x1, y1, x2, y2, pad)
-    # classify_card_rank thresholds (detect.py:127-131)
+    # classify_card_rank (detect.py:115-139), executed unmodified against a stand-in rank_model: 1 309 (top-1 name,
+    # confidence, detection class name) -> text decisions, thresholds probed on both sides in float32
+    assert len(g["classify_card_rank"]) > 1000 and g["classify_card_rank_empty"] == ["", ""]
+    for pred, conf, cname, want in g["classify_card_rank"]:
+        assert handoff.rank_text_from_top1(pred, conf, cname) == want, (pred, conf, cname, want)
     assert handoff.rank_text_from_top1("k", 0.41, "card1_rank") == "K"
     assert handoff.rank_text_from_top1("k", 0.39, "card1_rank") == ""
     assert handoff.rank_text_from_top1("10", 0.21, "turn_rank") == "10" and handoff.rank_text_from_top1("10", 0.19, "river_rank") == ""
