@@ -497,6 +497,15 @@ def run_ours(args, rank, world, local):
         c3 = bench_extra.config3(dev, B=256, cpu_images=0)
         configs["config3_nms_heavy"] = c3
         configs["config4_roi_4096"] = bench_extra.config4(dev)
+        # what plain torch fill / read kernels reach on THIS box for the step's bytes (context for the roofline fractions)
+        cal = bench_extra.calibration(dev)
+        wr, rd = cal["fill_315MB"]["GBps"], cal["read_reduce_1GiB_f32"]["GBps"]
+        written = BATCH * 3 * IMGSZ * IMGSZ * 4
+        calibration = {"fill_GBps": wr, "read_reduce_GBps": rd, "copy_GBps": cal["copy_1GiB"]["GBps"],
+                       "what": "torch fill_ of 315 MB / sum of 1 GiB / copy_ of 1 GiB on this GPU, cold L2",
+                       "bytes_written_per_step": written}
+    else:
+        calibration = None
 
     # ---- roofline of the dominant kernel (K1 letterbox), algorithmic bytes per launch ----
     peaks = {}
@@ -527,6 +536,13 @@ def run_ours(args, rank, world, local):
     rois_per_frame = len(ref["where"]) / BATCH if ref is not None else res.n_rois() / BATCH
     k5_required = rois_per_frame * (49152 + 12000)
     required = k1_bytes_frame + k2_required + 10_000 + k5_required
+    cal_floor = None
+    if calibration:
+        # the step's bytes at the rates plain streaming kernels reach on this box: net_in written at the fill rate, all
+        # other bytes (frames rows, class channels, survivors' sectors, ROI traffic) at the read rate
+        wbytes = calibration["bytes_written_per_step"]
+        floor_s = wbytes / (calibration["fill_GBps"] * 1e9) + (required * BATCH - wbytes) / (calibration["read_reduce_GBps"] * 1e9)
+        cal_floor = {"us_per_step": floor_s * 1e6, "frames_per_s_per_gpu": BATCH / floor_s}
     definition = k1_bytes_frame + k2_definition + 10_000 + 4 * 60_000                          # 11.77 MB
     kernels = {}
     bytes_per_launch = {"letterbox": BATCH * k1_bytes_frame, "decode_filter": BATCH * k2_required}
@@ -596,9 +612,14 @@ def run_ours(args, rank, world, local):
                                       "timed_in": "external event nodes around the kernel inside a single-stream CUDA graph "
                                                   "(includes the event-record nodes' own latency)"}},
             "kernels": kernels,
+            "calibration": calibration,
             "pipeline_roofline": {"required_bytes_per_frame": required,
                                   "roofline_frames_per_s_per_gpu": peak * 1e9 / required,
                                   "frac": (value / world) / (peak * 1e9 / required),
+                                  "calibrated_floor": None if cal_floor is None else
+                                  {**cal_floor, "frac": (value / world) / cal_floor["frames_per_s_per_gpu"],
+                                   "what": "the required bytes at this box's torch fill (writes) and read-reduce (reads) "
+                                           "rates from `calibration`, reads and writes serialised on the DRAM bus"},
                                   "what": "bytes the step must move: K1 7.22 MB + K2 nc*A*4 + 2 KB per survivor + K3/K4 ~10 KB + "
                                           "K5 ~61 KB per ROI",
                                   "survey_definition": {"bytes_per_frame": definition,
