@@ -178,11 +178,54 @@ def config_n3(dev, F=16):
     step = timed(lambda: sp(frames, head), flush=flush)
     res = sp(frames, head)
     torch.cuda.synchronize()
-    return {"frames": F, "slices_per_frame": sp.S, "letterbox_slices": k1, "sliced_step": step,
-            "frames_per_s": F / (step["us_median"] * 1e-6), "slices_per_s": F * sp.S / (step["us_median"] * 1e-6),
-            "merged_detections_per_frame": float(res.det.count.float().mean()),
-            "slice_detections_per_frame": float(sp.slice_det.count.float().sum() / F),
-            "l2": "L2 flushed between iterations; eager launches"}
+    out = {"frames": F, "slices_per_frame": sp.S, "letterbox_slices": k1, "sliced_step": step,
+           "frames_per_s": F / (step["us_median"] * 1e-6), "slices_per_s": F * sp.S / (step["us_median"] * 1e-6),
+           "merged_detections_per_frame": float(res.det.count.float().mean()),
+           "slice_detections_per_frame": float(sp.slice_det.count.float().sum() / F),
+           "l2": "L2 flushed between iterations; eager launches"}
+    # the form the reference's call has (SAHI defaults): + full-frame standard prediction, GREEDYNMM / IOS 0.5 merge
+    del sp
+    sd = m.SlicedPipeline(F, (1200, 1920), 64, conf=0.25, iou=0.7, merge_iou=0.5, device=dev, cap=1024, rois_per_frame=64,
+                          merge="greedy_nmm", match_metric="IOS", standard_pred=True)
+    hf, _ = synth.synth_head_from_labels(F, 64, in_hw=sd.full.in_hw, src_hw=(1200, 1920), seed=3, conf_thres=0.25)
+    hf = hf.to(dev)
+    step2 = timed(lambda: sd(frames, head, head_full=hf), flush=flush)
+    res2 = sd(frames, head, head_full=hf)
+    torch.cuda.synchronize()
+    out["sahi_defaults"] = {"sliced_step": step2, "frames_per_s": F / (step2["us_median"] * 1e-6),
+                            "merged_detections_per_frame": float(res2.det.count.float().mean()),
+                            "what": "12 slices + the full frame per frame, GREEDYNMM (IOS 0.5) merge, ROI crops"}
+    return out
+
+
+def config_n2(dev, n_frames=200, n_obj=30):
+    """ByteTrack (device Kalman + IoU costs, host association) on a synthetic sequence of padded NMS
+    outputs: tracker updates per second (host-bound: a few small launches and two small reads per frame)."""
+    import numpy as np
+    from manual_yolo_b200 import tracking
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(100, 1700, (n_obj, 2)); vel = rng.uniform(-5, 5, (n_obj, 2)); size = rng.uniform(40, 120, (n_obj, 2))
+    max_det = 300
+    dets = []
+    for f in range(n_frames):
+        c = pos + vel * f + rng.normal(0, 1.0, pos.shape)
+        keep = rng.random(n_obj) > 0.1
+        rows = np.concatenate([c - size / 2, c + size / 2, rng.uniform(0.3, 0.95, (n_obj, 1)), rng.integers(0, 5, (n_obj, 1))], 1)[keep]
+        pad = torch.zeros((1, max_det, 6)); pad[0, :rows.shape[0]] = torch.from_numpy(rows.astype(np.float32))
+        dets.append(m.Detections(pad.to(dev), torch.zeros((1, max_det), dtype=torch.int32, device=dev),
+                                 torch.tensor([rows.shape[0]], dtype=torch.int32, device=dev)))
+    trk = tracking.ByteTrack(device=dev, capacity=256, max_det=max_det)
+    for d in dets[:20]:
+        trk.update(d, 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ids = 0
+    for d in dets[20:]:
+        ids += int((trk.update(d, 0) >= 0).sum())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"frames": n_frames - 20, "objects": n_obj, "updates_per_s": (n_frames - 20) / dt, "ms_per_update": 1e3 * dt / (n_frames - 20),
+            "tracked_detections": ids, "live_tracks": len(trk.tracked), "what": "wall clock, one frame per update, host-bound"}
 
 
 def config1(dev):
@@ -265,7 +308,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_extra.json"))
     ap.add_argument("--b3", type=int, default=256)
-    ap.add_argument("--only", default="", help="comma list of: calibration,config3,config4,config1,n3,cpu (default: all)")
+    ap.add_argument("--only", default="", help="comma list of: calibration,config3,config4,config1,n3,n2,k1half,cpu (default: all)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     parts = {"calibration": ("calibration", lambda: calibration(dev)),
@@ -273,6 +316,7 @@ def main():
              "config4": ("config4_roi_4096", lambda: config4(dev)),
              "config1": ("config1_single_frame", lambda: config1(dev)),
              "n3": ("n3_sliced_prediction", lambda: config_n3(dev)),
+             "n2": ("n2_bytetrack", lambda: config_n2(dev)),
              "k1half": ("k1_letterbox_f32_vs_f16", lambda: k1_half(dev)),
              "cpu": ("cpu_oracle_threads", lambda: cpu_threads(dev))}
     only = [x for x in args.only.split(",") if x] or list(parts)
