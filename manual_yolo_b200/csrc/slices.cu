@@ -104,6 +104,8 @@ extern "C" int b200yolo_gather_slice_detections(const float* det, const int* det
 namespace {
 
 constexpr int kNmmMax = 8192;     // candidates per frame ((n_slices + 1) * max_det, padded to a power of two)
+constexpr int kNmmFast = 512;     // frames with at most this many candidates take the parallel form (bit rows in shared memory)
+constexpr int kNmmW = kNmmFast / 64;
 
 __device__ __forceinline__ float nmm_metric_f32(const float* a, float area_a, const float* b, float area_b, int ios) {
   const float w = fmaxf(__fsub_rn(fminf(a[2], b[2]), fmaxf(a[0], b[0])), 0.f);
@@ -157,6 +159,119 @@ __global__ void __launch_bounds__(256) greedy_nmm_kernel(const float* __restrict
       __syncthreads();
     }
   auto idx_of = [&](int r) { return (int)(0xffffu - (unsigned)(key[r] & 0xffffu)); };
+  if (n <= kNmmFast) {
+    // ---- fast path (what a frame's slices + full frame produce after their own NMS: a few hundred candidates) ----
+    // greedy_nmm is greedy NMS with a merge step: candidate q is a keeper iff no EARLIER KEEPER r matches it
+    // (match = the fp32 test on the ORIGINAL boxes), and a keeper merges the candidates it matches that no earlier
+    // keeper took, in rank order.  So: (1) all pair matches up front, in parallel, as bit rows; (2) the keeper set as
+    // the fixed point K = all & ~S(K), S(K) = union of the keepers' rows (a candidate is final after the length of its
+    // chain of matches: 2-3 rounds); (3) one thread per keeper does its own merge list.  The serial form below spends
+    // three CTA barriers per keeper.
+    float* sbox = reinterpret_cast<float*>(key + kNmmFast);                                   // [kNmmFast][6] rank order
+    unsigned long long* M = reinterpret_cast<unsigned long long*>(sbox + kNmmFast * 6);     // [kNmmFast][kNmmW] match rows
+    __shared__ unsigned long long Kw[kNmmW], Sw[kNmmW];
+    __shared__ int kbase[kNmmW + 1], changed, nact;
+    __shared__ short act[kNmmFast];
+    for (int r = tid; r < n; r += NT) {
+      const float* b = rows + idx_of(r) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) sbox[r * 6 + c] = b[c];
+    }
+    if (tid < kNmmW) {
+      const int lo = tid * 64;
+      Kw[tid] = n >= lo + 64 ? ~0ull : (n > lo ? ((1ull << (n - lo)) - 1ull) : 0ull);
+      Sw[tid] = 0ull;
+    }
+    if (tid == 0) nact = 0;
+    __syncthreads();
+    for (int r = tid; r < n; r += NT) {                        // (1) row r: the later candidates r matches
+      const float* bi = sbox + r * 6;
+      const float area_i = __fmul_rn(__fsub_rn(bi[2], bi[0]), __fsub_rn(bi[3], bi[1]));
+      bool any = false;
+      for (int w = 0; w < kNmmW; ++w) {
+        unsigned long long bits = 0ull;
+        const int q1 = min(n, (w + 1) * 64);
+        for (int q = max(r + 1, w * 64); q < q1; ++q) {
+          const float* bj = sbox + q * 6;
+          if (!agnostic && bj[5] != bi[5]) continue;
+          const float area_j = __fmul_rn(__fsub_rn(bj[2], bj[0]), __fsub_rn(bj[3], bj[1]));
+          if (!(nmm_metric_f32(bi, area_i, bj, area_j, ios) < thr32)) bits |= 1ull << (q & 63);   // NaN counts as matched
+        }
+        M[r * kNmmW + w] = bits;
+        any = any || bits != 0ull;
+      }
+      if (any) act[atomicAdd(&nact, 1)] = (short)r;            // rows that can consume anything (few)
+    }
+    __syncthreads();
+    const int na = nact;
+    for (;;) {                                                 // (2) fixed point over the keeper set
+      if (tid == 0) changed = 0;
+      for (int a = tid; a < na; a += NT) {
+        const int r = act[a];
+        if ((Kw[r >> 6] >> (r & 63)) & 1ull)
+          for (int w = r >> 6; w < kNmmW; ++w) { const unsigned long long v = M[r * kNmmW + w]; if (v) atomicOr(&Sw[w], v); }
+      }
+      __syncthreads();
+      if (tid < kNmmW) {
+        const int lo = tid * 64;
+        const unsigned long long valid = n >= lo + 64 ? ~0ull : (n > lo ? ((1ull << (n - lo)) - 1ull) : 0ull);
+        const unsigned long long kn = valid & ~Sw[tid];
+        if (kn != Kw[tid]) { Kw[tid] = kn; changed = 1; }
+        Sw[tid] = 0ull;
+      }
+      __syncthreads();
+      if (!changed) break;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      int acc = 0;
+      for (int w = 0; w < kNmmW; ++w) { kbase[w] = acc; acc += __popcll(Kw[w]); }
+      kbase[kNmmW] = acc;
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += NT) {                        // (3) one thread per keeper
+      const unsigned long long kw = Kw[r >> 6];
+      if (!((kw >> (r & 63)) & 1ull)) continue;
+      const int kk = kbase[r >> 6] + __popcll(kw & ((1ull << (r & 63)) - 1ull));
+      if (kk >= max_det) continue;
+      const float* bi = sbox + r * 6;
+      double mb[4] = {(double)bi[0], (double)bi[1], (double)bi[2], (double)bi[3]};
+      float mscore = bi[4], mcls = bi[5];
+      bool mine = false;
+      for (int w = r >> 6; w < kNmmW; ++w) mine = mine || M[r * kNmmW + w] != 0ull;
+      if (mine) {
+        for (int w = r >> 6; w < kNmmW; ++w) {
+          unsigned long long bits = M[r * kNmmW + w];
+          if (!bits) continue;
+          for (int a = 0; a < na; ++a) {                       // minus what earlier keepers consumed
+            const int r2 = act[a];
+            if (r2 < r && ((Kw[r2 >> 6] >> (r2 & 63)) & 1ull)) bits &= ~M[r2 * kNmmW + w];
+          }
+          while (bits) {                                       // rank ascending = best first
+            const int q = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1ull;
+            const float* bj = sbox + q * 6;
+            if (nmm_metric_f64(mb, bj, ios) > thr64) {
+              mb[0] = fmin(mb[0], (double)bj[0]); mb[1] = fmin(mb[1], (double)bj[1]);
+              mb[2] = fmax(mb[2], (double)bj[2]); mb[3] = fmax(mb[3], (double)bj[3]);
+              if (!(mscore > bj[4])) mcls = bj[5];             // category of the higher score (the later one on a tie)
+              mscore = fmaxf(mscore, bj[4]);
+            }
+          }
+        }
+      }
+      float* o = out + ((int64_t)f * max_det + kk) * 6;
+      o[0] = (float)mb[0]; o[1] = (float)mb[1]; o[2] = (float)mb[2]; o[3] = (float)mb[3]; o[4] = mscore; o[5] = mcls;
+      out_src[(int64_t)f * max_det + kk] = cand_src[(int64_t)f * cap + idx_of(r)];
+      if (roi_cnt) {
+        const int c = (int)mcls;
+        if (c >= 0 && c < roi_nc && ((roi_mask[c >> 5] >> (c & 31)) & 1u)) atomicAdd(&roi_s, 1);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { out_count[f] = min(kbase[kNmmW], max_det); if (roi_cnt) roi_cnt[f] = roi_s; }
+    return;
+  }
   for (int r = 0; r < n; ++r) {
     const int i = idx_of(r);
     if (consumed[i]) continue;                                   // uniform: read after a barrier
