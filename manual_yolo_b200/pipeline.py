@@ -201,6 +201,10 @@ class Pipeline:
                                         max_nms=self.max_nms, max_wh=self.max_wh, scale=self.scale,
                                         roi_mask=self.roi_mask, roi_nc=self.nc, roi_cnt=self.roi_cnt)
             cand_count = self.cands.count
+        if not getattr(self, "roi_stage", True):     # detections only (SlicedPipeline's full-frame pass: the ROIs are cut
+            t(None)                                   # from the MERGED detections); the ROI outputs keep their last contents
+            return PipelineResult(self.net_in, det, cand_count, self.roi_out[0], self.roi_out[1], self.roi_out[2],
+                                  self.roi_out[3], self.roi_out[4], self.cap)
         t("roi_crop_resize")
         ro = api.rois_from_detections(self._roi_frames, det, self.roi_cnt, self.roi_mask, self.nc, self.roi_cap, self.pad,
                                       self.roi_size, out=self.roi_out)
@@ -524,6 +528,9 @@ class SlicedPipeline:
         self.full = Pipeline(self.F, self.frame_hw, nc, imgsz=imgsz, conf=conf, iou=iou, max_det=max_det, agnostic=agnostic,
                              max_nms=max_nms, max_wh=max_wh, roi_classes=roi_classes, rois_per_frame=1, strides=strides,
                              device=dev, cap=cap) if self.standard_pred else None
+        if self.full is not None:
+            self.full.roi_stage = False                                        # its ROI kernels would be wasted work
+            self._full_stream = torch.cuda.Stream(device=dev)                  # the full-frame pass runs beside the slices
         mcap = (self.S + (1 if self.standard_pred else 0)) * max_det
         self.mcands = api.Candidates(torch.empty((self.F, mcap, 6), dtype=torch.float32, device=dev),
                                      torch.empty((self.F, mcap), dtype=torch.int32, device=dev),
@@ -551,6 +558,15 @@ class SlicedPipeline:
         ``head_full`` (F, 64+nc, A_full): the Detect head of the letterboxed full frames (``standard_pred=True``).
         Returns the MERGED per-frame detections (frame pixels); ``det.anchor`` = slice * max_det + rank of the kept
         box (slice index S = the full-frame prediction)."""
+        full_det = None
+        if self.standard_pred:
+            if head_full is None:
+                raise ValueError("standard_pred=True needs head_full: the Detect head of the letterboxed full frames")
+            cur = torch.cuda.current_stream()
+            self._full_stream.wait_stream(cur)                                 # fork: independent of the slice branch
+            with torch.cuda.stream(self._full_stream):
+                self.full_result = self.full(frames, head_full)
+            full_det = self.full_result.det
         self.preprocess(frames)
         if self.fused:
             api.decode_and_filter(head, self.strides, self.conf, level_hw=self.level_hw, cap=self.cap, out=self.cands,
@@ -566,12 +582,8 @@ class SlicedPipeline:
                                  scale=self.scale)
             cand_count = self.cands.count
         self.slice_det = det
-        full_det = None
         if self.standard_pred:
-            if head_full is None:
-                raise ValueError("standard_pred=True needs head_full: the Detect head of the letterboxed full frames")
-            self.full_result = self.full(frames, head_full)
-            full_det = self.full_result.det
+            torch.cuda.current_stream().wait_stream(self._full_stream)         # join
         api.gather_slice_detections(det, self.slices, self.F, out=self.mcands, full_det=full_det)
         if self.merge == "greedy_nmm":
             merged = api.greedy_nmm(self.mcands, self.mws.det, self.match_metric, self.merge_iou, self.agnostic,
