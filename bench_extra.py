@@ -192,7 +192,21 @@ def config_n3(dev, F=16):
     step2 = timed(lambda: sd(frames, head, head_full=hf), flush=flush)
     res2 = sd(frames, head, head_full=hf)
     torch.cuda.synchronize()
-    out["sahi_defaults"] = {"sliced_step": step2, "frames_per_s": F / (step2["us_median"] * 1e-6),
+    try:                                                   # the same step as one CUDA graph (how a service would drive it)
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            sd(frames, head, head_full=hf)
+        torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            sd(frames, head, head_full=hf)
+        step2g = timed(lambda: g.replay(), flush=flush)
+        step2g["frames_per_s"] = F / (step2g["us_median"] * 1e-6)
+    except Exception as e:                                 # noqa: BLE001 -- reported, not hidden
+        step2g = {"error": repr(e)[:200]}
+    out["sahi_defaults"] = {"sliced_step": step2, "sliced_step_cuda_graph": step2g, "frames_per_s": F / (step2["us_median"] * 1e-6),
                             "merged_detections_per_frame": float(res2.det.count.float().mean()),
                             "what": "12 slices + the full frame per frame, GREEDYNMM (IOS 0.5) merge, ROI crops"}
     return out
